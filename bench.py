@@ -1,0 +1,387 @@
+#!/usr/bin/env python3
+"""bench.py — PARAM EmbeddingBag + DLRM all-to-all hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N = 1 (default): BASELINE.json configs[1] — 256-table batched EmbeddingBag fwd+bwd, dim 128, global
+batch 65536, bag 20, Zipf alpha=1.15 — with rows/table scaled to fit one GPU (256 x 10M x 128 fp32 is
+1.31 TB).  A step = one forward over all tables + one backward (scatter-add of the
+pooled gradient into the table arena, fused SGD).  Prints ONE JSON line.
+N > 1: see bench_dist (DLRM table-parallel step: lookup -> fused all-to-all -> transpose -> scatter-add).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "embeddingbag_lookups_per_sec"
+UNIT = "lookups/s"
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--tables", type=int, default=256)
+    ap.add_argument("--rows", type=int, default=1_000_000, help="rows per table (scaled to fit HBM)")
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--bag", type=int, default=20)
+    ap.add_argument("--alpha", type=float, default=1.15)
+    ap.add_argument("--fwd-algo", default="auto")
+    ap.add_argument("--bwd-algo", default="auto")
+    ap.add_argument("--lr", type=float, default=1e-6)
+    ap.add_argument("--cpu-tables", type=int, default=4, help="tables in the CPU baseline sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-group", type=int, default=16, help="tables per H2D/kernel/D2H pipeline group")
+    return ap.parse_args(argv)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(T, B, L, D):
+    """fwd = B*L*(D*4+8) + B*8 + B*D*4 per table; bwd = B*L*(2*D*4+8) + B*D*4."""
+    fwd = T * (B * L * (D * 4 + 8) + B * 8 + B * D * 4)
+    bwd = T * (B * L * (2 * D * 4 + 8) + B * D * 4)
+    return fwd, bwd
+
+
+def ev_time(fn, iters, stream=None):
+    """CUDA-event time of `iters` back-to-back calls of fn on the current stream -> ms per call."""
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(iters):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(args, dev):
+    from param_b200 import ops
+    from param_b200.compute.pt.pytorch_emb import zipf_cdf
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    free, total = torch.cuda.mem_get_info(dev)
+    fixed = T * B * L * 8 + (T * B + 1) * 8 + 2 * T * B * D * 4 + (6 << 30)  # idx, off, out, grad, slack
+    rows = args.rows
+    max_rows = int((free - fixed) // (T * D * 4))
+    scaled = False
+    if rows > max_rows:
+        rows, scaled = max(max_rows // 1000 * 1000, 1000), True
+    arena = ops.TableArena.allocate([rows] * T, D, dev)
+    ops.fill_uniform_(arena.weights, -(1.0 / rows) ** 0.5, (1.0 / rows) ** 0.5, seed=2026)
+    idx = torch.empty(T * B * L, dtype=torch.int64, device=dev)
+    if args.alpha > 0:
+        cdf = torch.from_numpy(zipf_cdf(args.alpha, rows)).to(dev)
+    else:
+        cdf = torch.linspace(1.0 / rows, 1.0, rows, dtype=torch.float64, device=dev)
+    for t in range(T):
+        ops.fill_zipf_indices_(idx[t * B * L:(t + 1) * B * L], L, cdf, seed=1000 + t, dedupe=args.alpha > 0)
+    off = torch.arange(T * B + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
+    return arena, idx, off, rows, scaled
+
+
+def run_b200(args):
+    from param_b200 import _cabi, ops
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    arena, idx, off, rows, scaled = build_workload(args, dev)
+    out = torch.empty((B, T * D), dtype=torch.float32, device=dev)
+    lookups = T * B * L
+    bwd_algo = "sorted" if args.bwd_algo == "auto" else args.bwd_algo
+
+    def fwd():
+        ops.tbe_forward(arena, idx, off, B, layout="BTD", algo=args.fwd_algo, out=out)
+
+    def bwd():
+        # the pooled output doubles as the incoming gradient (same shape; saves 8.6 GB of HBM)
+        ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, layout="BTD",
+                         scale=-args.lr, algo=bwd_algo)
+
+    def step():
+        fwd()
+        bwd()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _cabi.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_step = ev_time(step, args.steps)
+    launches = _cabi.launch_count() - n0
+    if world > 1:
+        import torch.distributed as dist
+        tmax = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_step = float(tmax.item())
+        dist.barrier()
+    # per-kernel durations for the roofline (same process, CUDA events on the launching stream)
+    ms_fwd = ev_time(fwd, args.steps)
+    ms_bwd = ev_time(bwd, args.steps)
+    ms_fwd_direct = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="direct", out=out), args.steps)
+    ms_bwd_other = None
+    other = "atomic" if bwd_algo == "sorted" else "sorted"
+    try:
+        ms_bwd_other = ev_time(lambda: ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
+                                                        layout="BTD", scale=-args.lr, algo=other),
+                               max(2, args.steps // 2))
+    except Exception as exc:  # noqa: BLE001
+        ms_bwd_other = f"failed: {exc}"
+
+    peak, peak_src = measured_peaks()
+    fwd_bytes, bwd_bytes = algorithmic_bytes(T, B, L, D)
+    dominant = "fwd" if ms_fwd >= ms_bwd else "bwd"
+    dom_bytes, dom_ms = (fwd_bytes, ms_fwd) if dominant == "fwd" else (bwd_bytes, ms_bwd)
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(dominant)
+        except Exception:
+            traffic = None
+
+    def roof(nbytes, ms):
+        a = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(a / peak, 4), "peak_source": peak_src}
+
+    res = {
+        "metric": METRIC, "value": world * lookups / (ms_step * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"cfg2: {T}-table batched EmbeddingBag fwd+bwd, {rows} rows x {D} dim per table "
+                               f"(scaled from 10M rows to fit 180 GB HBM{'; further scaled to free memory' if scaled else ''}), "
+                               f"global batch {B}, bag {L}, Zipf alpha={args.alpha}, int64 indices",
+                   "tables": T, "rows_per_table": rows, "dim": D, "batch": B, "bag": L, "alpha": args.alpha,
+                   "fwd_algo": args.fwd_algo, "bwd_algo": bwd_algo,
+                   "l2_policy": "inputs larger than L2 (arena %.1f GB, pooled output %.1f GB)" %
+                                (arena.weights.numel() * 4 / 1e9, out.numel() * 4 / 1e9),
+                   "parallelism": "replicas" if world > 1 else "single"},
+        "gpu_launches": int(launches),
+        "roofline": dict(roof(dom_bytes, dom_ms), kernel=dominant, traffic=traffic,
+                         algorithmic_bytes=dom_bytes, ms=round(dom_ms, 4)),
+        "kernels": {"fwd": dict(roof(fwd_bytes, ms_fwd), ms=round(ms_fwd, 4), lookups_per_s=lookups / ms_fwd * 1e3,
+                                param_bw_gbs=round(lookups * D * 4 / ms_fwd / 1e6, 1)),
+                    "fwd_direct_ms": round(ms_fwd_direct, 4),
+                    "bwd": dict(roof(bwd_bytes, ms_bwd), ms=round(ms_bwd, 4), algo=bwd_algo),
+                    f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4)},
+        "clocks": clk.summary(),
+    }
+    if rank == 0 and not args.skip_e2e:
+        res["e2e"] = run_e2e(args, arena, idx, off, lookups)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        res["cpu_baseline"] = cpu_baseline(args, arena, idx, rows, backward=True)
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, arena, idx, off, lookups):
+    """Same step through the C-ABI host-buffer entry: indices/offsets start in pinned HOST memory,
+    pooled vectors end in pinned HOST memory; H2D + kernels + D2H are all inside the timed region."""
+    import ctypes as C
+    from param_b200 import _cabi
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    lib = _cabi.load()
+    g = min(args.e2e_group, T)
+    h_idx = torch.empty(idx.numel(), dtype=torch.int64).pin_memory()
+    h_off = torch.empty(off.numel(), dtype=torch.int64).pin_memory()
+    h_idx.copy_(idx)
+    h_off.copy_(off)
+    h_out = torch.empty((B, T * D), dtype=torch.float32).pin_memory()
+    tro_h = arena.row_offsets.cpu()
+    ctx = C.c_void_p()
+    _cabi.check(lib.pb200_host_ctx_create(C.byref(ctx), g * B * L + 16, g * B, D), "host_ctx_create")
+
+    def call():
+        _cabi.check(lib.pb200_tbe_step_host(ctx, arena.weights.data_ptr(), arena.row_offsets.data_ptr(),
+                                            tro_h.data_ptr(), T, D, h_idx.data_ptr(), h_idx.numel(),
+                                            h_off.data_ptr(), B, 0, h_out.data_ptr(), 0, g,
+                                            1, C.c_float(-args.lr)), "tbe_step_host")
+
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = max(3, args.steps // 2)
+    for _ in range(n):
+        call()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    lib.pb200_host_ctx_destroy(ctx)
+    return {"value": lookups / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(h_idx.numel() * 8 + h_off.numel() * 8),
+            "d2h_bytes_per_step": int(h_out.numel() * 4),
+            "path": "pb200_tbe_step_host (C ABI, pinned host buffers, %d-table pipeline groups): "
+                    "H2D indices+offsets -> lookup fwd -> D2H pooled -> scatter-add bwd" % g}
+
+
+def cpu_baseline(args, arena, idx, rows, backward):
+    """Reference CPU path (torch.nn.EmbeddingBag on the host cores, measure_cpu loop shape) on a
+    bounded sample: the first --cpu-tables tables of the same workload, same indices."""
+    from oracle import ref_torch_cpu  # bench-only import of oracle/
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    n = min(args.cpu_tables, T)
+    ws = [arena.table(t).cpu() for t in range(n)]
+    ids = [idx[t * B * L:(t + 1) * B * L].cpu() for t in range(n)]
+    offs = [torch.arange(B, dtype=torch.int64) * L for _ in range(n)]
+    sec, threads = ref_torch_cpu.time_embeddingbag_cpu(ws, ids, offs, steps=3, warmups=1, backward=backward)
+    return {"value": n * B * L / sec, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(),
+            "kind": "reference",
+            "sample": f"torch.nn.EmbeddingBag(mode=sum, sparse=True) fwd+bwd on the host, first {n} of {T} tables "
+                      f"({rows} rows x {D}), same Zipf indices, 3 steps after 1 warm-up (measure_cpu loop, "
+                      "train/compute/pt/pytorch_emb.py:37-45)",
+            "ms_per_step_sample": sec * 1e3}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, on a
+    bounded sample of the same workload.  Rank 0 only."""
+    from oracle import ref_torch_cpu
+    from param_b200.compute.pt.pytorch_emb import zipf_cdf
+    import numpy as np
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    rows = args.rows
+    n = min(args.cpu_tables, T)
+    rng = np.random.default_rng(2026)
+    cdf = zipf_cdf(args.alpha, rows) if args.alpha > 0 else np.linspace(1.0 / rows, 1.0, rows)
+    ws, ids, offs = [], [], []
+    for t in range(n):
+        ws.append((torch.rand(rows, D) * 2 - 1) * (1.0 / rows) ** 0.5)
+        ids.append(torch.from_numpy(np.searchsorted(cdf, rng.random(B * L), side="right").clip(0, rows - 1).astype(np.int64)))
+        offs.append(torch.arange(B, dtype=torch.int64) * L)
+    sec, threads = ref_torch_cpu.time_embeddingbag_cpu(ws, ids, offs, steps=args.steps, warmups=args.warmup,
+                                                       backward=True)
+    v = n * B * L / sec
+    sample = (f"first {n} of {T} tables per step ({rows} rows x {D}, batch {B}, bag {L}, Zipf {args.alpha}), "
+              "torch.nn.EmbeddingBag CPU fwd+bwd, all host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 sample: {sample}", "tables": T, "rows_per_table": rows, "dim": D,
+                   "batch": B, "bag": L, "alpha": args.alpha},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(),
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus}")
+    if world > 1:
+        from bench_dist import run_dist
+        run_dist(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

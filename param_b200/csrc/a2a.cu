@@ -1,0 +1,452 @@
+// a2a.cu — single-node all-to-all as direct peer-HBM writes over NVLink 5 / NVSwitch (sm_100a).
+//
+// Replaces, for the DLRM path only:
+//   dist.all_to_all_single(out, in, out_splits, in_splits)
+//       train/comms/pt/pytorch_dist_backend.py:330-357 (all_to_all_single), :262-328 (all_to_allv)
+//   All2Allv_Req/All2Allv_Wait + torch.cat either side of it
+//       train/comms/pt/dlrm.py:86-218, :1253
+//
+// Every rank maps every peer's "window" (data) and "pad" (flags).  ONE kernel per rank and per
+// collective does, for each destination j, a 2-D strided copy
+//     peer_window[j] + dst_off[j] + r*dst_stride[j] + c   <-   src[j] + r*src_stride[j] + c
+// with 16 B loads from local HBM and 16 B stores straight into the peer's HBM, so the per-rank
+// output permute ([T,N,E] -> [lN, T_global*E] and its transpose) costs no extra pass: it is the
+// address calculation of the push.  all_to_all_single is the 1-row case.
+//
+// Protocol per call (epoch e, monotonically increasing, kept in device memory so that a captured
+// CUDA graph replays correctly):
+//   1. ready : rank j tells every source r "my window may be overwritten for epoch e" and where
+//              r's block goes (pad[r].ready_payload[j], pad[r].ready_epoch[j], st.release.sys).
+//              This is what posting the receive buffer is for NCCL: the kernel runs after all of
+//              j's earlier stream work, so earlier readers of the window have finished.
+//   2. push  : every CTA, for each destination (rotated by rank and CTA so that all W-1 NVSwitch
+//              ports are busy at once), waits for that destination's ready flag (ld.acquire.sys
+//              on its OWN pad — local memory), then copies its slice.
+//   3. done  : per destination, the last CTA to finish (device-scope counter) executes
+//              fence.acq_rel.sys and st.release.sys pad[j].done_epoch[me] = e.
+//   4. wait  : the last CTA of the grid spins until done_epoch[r] >= e for all sources r, then
+//              publishes the new epoch.  Kernel completion == c10d Work.wait() semantics.
+// No CTA ever waits on another CTA of the same grid, so the grid need not be co-resident.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace pb200 {
+
+struct SignalPad {
+    unsigned long long ready_epoch[PB200_A2A_MAX_RANKS];
+    unsigned long long ready_payload[PB200_A2A_MAX_RANKS];
+    unsigned long long done_epoch[PB200_A2A_MAX_RANKS];
+};
+static_assert(sizeof(SignalPad) <= PB200_A2A_SIGNAL_BYTES, "signal pad too small");
+
+struct PeerCopy {
+    const unsigned char *src;   // local
+    long long src_stride;       // bytes between rows
+    long long dst_stride;       // bytes between rows in the destination window
+    long long run_bytes;        // contiguous bytes per row
+    long long rows;
+};
+
+struct A2AArgs {
+    unsigned char *peer_data[PB200_A2A_MAX_RANKS];
+    SignalPad *peer_pad[PB200_A2A_MAX_RANKS];
+    PeerCopy copy[PB200_A2A_MAX_RANKS];            // what I send to each destination
+    long long recv_off[PB200_A2A_MAX_RANKS];       // where source r must write inside MY window
+    unsigned long long *epoch;                      // device: last completed epoch
+    unsigned *peer_cnt;                             // device [W]: CTAs finished per destination
+    unsigned *grid_cnt;                             // device: CTAs finished overall
+    int rank;
+    int world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 ld_src_v4(const int4 *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_peer_v4(int4 *p, const int4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+constexpr int kA2AThreads = 512;
+constexpr int kA2AUnroll = 4;
+
+// copy units [u0, u1) of one destination; a unit is UNIT bytes; run_units = units per row
+template <int UNIT>
+__device__ __forceinline__ void copy_units(unsigned char *dst, long long dst_stride,
+                                           const unsigned char *src, long long src_stride,
+                                           long long run_units, long long u0, long long u1) {
+    if (UNIT == 16) {
+        long long u = u0 + threadIdx.x;
+        const long long step = (long long)kA2AThreads;
+        // unrolled main loop: kA2AUnroll independent 16 B loads in flight per thread
+        for (; u + (kA2AUnroll - 1) * step < u1; u += kA2AUnroll * step) {
+            int4 v[kA2AUnroll];
+            long long doff[kA2AUnroll];
+#pragma unroll
+            for (int k = 0; k < kA2AUnroll; ++k) {
+                const long long uu = u + k * step;
+                const long long r = uu / run_units;
+                const long long c = uu - r * run_units;
+                v[k] = ld_src_v4((const int4 *)(src + r * src_stride) + c);
+                doff[k] = r * dst_stride + c * 16;
+            }
+#pragma unroll
+            for (int k = 0; k < kA2AUnroll; ++k) st_peer_v4((int4 *)(dst + doff[k]), v[k]);
+        }
+        for (; u < u1; u += step) {
+            const long long r = u / run_units;
+            const long long c = u - r * run_units;
+            const int4 v = ld_src_v4((const int4 *)(src + r * src_stride) + c);
+            st_peer_v4((int4 *)(dst + r * dst_stride + c * 16), v);
+        }
+    } else {
+        for (long long u = u0 + threadIdx.x; u < u1; u += kA2AThreads) {
+            const long long r = u / run_units;
+            const long long c = u - r * run_units;
+            if (UNIT == 4)
+                *(int *)(dst + r * dst_stride + c * 4) = *(const int *)(src + r * src_stride + c * 4);
+            else
+                dst[r * dst_stride + c] = src[r * src_stride + c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, const int unit_log2) {
+    __shared__ unsigned long long s_epoch;
+    __shared__ unsigned long long s_payload;
+    const int W = a.world;
+    const int me = a.rank;
+    SignalPad *my_pad = a.peer_pad[me];
+
+    if (threadIdx.x == 0) s_epoch = *(volatile unsigned long long *)a.epoch + 1ull;
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+
+    // 1. ready: CTA 0 posts my receive offsets to every source
+    if (blockIdx.x == 0 && threadIdx.x < W && (int)threadIdx.x != me) {
+        SignalPad *pp = a.peer_pad[threadIdx.x];
+        st_relaxed_sys(&pp->ready_payload[me], (unsigned long long)a.recv_off[threadIdx.x]);
+        st_release_sys(&pp->ready_epoch[me], e);
+    }
+
+    // 2. push
+    const long long unit = 1ll << unit_log2;
+    for (int k = 0; k < W; ++k) {
+        // rotation: self first (no handshake needed, overlaps the ready round trip), then
+        // destinations staggered by rank and by CTA so every NVSwitch port is busy
+        const int j = (k == 0) ? me : (me + 1 + ((k - 1) + blockIdx.x) % (W - 1)) % W;
+        const PeerCopy pc = a.copy[j];
+        const long long total_units = (pc.run_bytes >> unit_log2) * pc.rows;
+        long long dst_off;
+        if (j == me) {
+            dst_off = a.recv_off[me];
+        } else {
+            if (threadIdx.x == 0) {
+                while (ld_acquire_sys(&my_pad->ready_epoch[j]) < e) {
+                }
+                s_payload = ld_relaxed_sys(&my_pad->ready_payload[j]);
+            }
+            __syncthreads();
+            dst_off = (long long)s_payload;
+        }
+        if (total_units > 0) {
+            // contiguous slice of units per CTA (keeps each CTA's stores in long runs)
+            const long long per = (total_units + gridDim.x - 1) / gridDim.x;
+            const long long u0 = per * blockIdx.x;
+            const long long u1 = min(u0 + per, total_units);
+            if (u0 < u1) {
+                unsigned char *dst = a.peer_data[j] + dst_off;
+                const long long run_units = pc.run_bytes >> unit_log2;
+                if (unit_log2 == 4)
+                    copy_units<16>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+                else if (unit_log2 == 2)
+                    copy_units<4>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+                else
+                    copy_units<1>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+            }
+        }
+        (void)unit;
+        // 3. done: last CTA for this destination signals it
+        __syncthreads();
+        if (threadIdx.x == 0 && j != me) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(&a.peer_cnt[j], 1u);
+            if (prev == gridDim.x - 1) {
+                a.peer_cnt[j] = 0;
+                __threadfence_system();
+                st_release_sys(&a.peer_pad[j]->done_epoch[me], e);
+            }
+        }
+    }
+
+    // 4. wait: last CTA of the grid waits for all sources, then publishes the epoch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(a.grid_cnt, 1u);
+        if (prev == gridDim.x - 1) {
+            for (int r = 0; r < W; ++r) {
+                if (r == me) continue;
+                while (ld_acquire_sys(&my_pad->done_epoch[r]) < e) {
+                }
+            }
+            *a.grid_cnt = 0;
+            *(volatile unsigned long long *)a.epoch = e;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+struct pb200_a2a_comm {
+    int rank;
+    int world;
+    long long window_bytes;
+    unsigned char *peer_data[PB200_A2A_MAX_RANKS];
+    SignalPad *peer_pad[PB200_A2A_MAX_RANKS];
+    unsigned long long *d_epoch;
+    unsigned *d_peer_cnt;
+    unsigned *d_grid_cnt;
+    int max_ctas;
+};
+
+extern "C" int pb200_a2a_comm_create(pb200_a2a_comm **comm, int32_t rank, int32_t world,
+                                     void *const *peer_data, void *const *peer_signal,
+                                     int64_t window_bytes) {
+    if (!comm || !peer_data || !peer_signal) return PB200_EINVAL;
+    if (world < 1 || world > PB200_A2A_MAX_RANKS || rank < 0 || rank >= world || window_bytes < 0)
+        return PB200_EINVAL;
+    pb200_a2a_comm *c = (pb200_a2a_comm *)calloc(1, sizeof(pb200_a2a_comm));
+    if (!c) return PB200_EINVAL;
+    c->rank = rank;
+    c->world = world;
+    c->window_bytes = window_bytes;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_data[r] || !peer_signal[r]) {
+            free(c);
+            return PB200_EINVAL;
+        }
+        c->peer_data[r] = (unsigned char *)peer_data[r];
+        c->peer_pad[r] = (SignalPad *)peer_signal[r];
+    }
+    unsigned char *blk = nullptr;
+    cudaError_t e = cudaMalloc(&blk, 256);
+    if (e != cudaSuccess) {
+        free(c);
+        return (int)e;
+    }
+    e = cudaMemset(blk, 0, 256);
+    if (e != cudaSuccess) {
+        cudaFree(blk);
+        free(c);
+        return (int)e;
+    }
+    c->d_epoch = (unsigned long long *)blk;
+    c->d_grid_cnt = (unsigned *)(blk + 8);
+    c->d_peer_cnt = (unsigned *)(blk + 64);
+    const char *env = getenv("PB200_A2A_CTAS");
+    c->max_ctas = env ? atoi(env) : 0;
+    *comm = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_a2a_comm_destroy(pb200_a2a_comm *comm) {
+    if (!comm) return PB200_OK;
+    if (comm->d_epoch) cudaFree(comm->d_epoch);
+    free(comm);
+    return PB200_OK;
+}
+
+static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st) {
+    for (int r = 0; r < c->world; ++r) {
+        a.peer_data[r] = c->peer_data[r];
+        a.peer_pad[r] = c->peer_pad[r];
+    }
+    a.epoch = c->d_epoch;
+    a.peer_cnt = c->d_peer_cnt;
+    a.grid_cnt = c->d_grid_cnt;
+    a.rank = c->rank;
+    a.world = c->world;
+    // common alignment of everything that moves -> copy unit
+    uintptr_t bits = 0;
+    for (int r = 0; r < c->world; ++r) {
+        const PeerCopy &pc = a.copy[r];
+        if (pc.rows == 0 || pc.run_bytes == 0) continue;
+        bits |= (uintptr_t)pc.src | (uintptr_t)pc.run_bytes;
+        if (pc.rows > 1) bits |= (uintptr_t)pc.src_stride | (uintptr_t)pc.dst_stride;
+    }
+    for (int r = 0; r < c->world; ++r) bits |= (uintptr_t)a.recv_off[r] | (uintptr_t)c->peer_data[r];
+    const int unit_log2 = (bits & 15) == 0 ? 4 : ((bits & 3) == 0 ? 2 : 0);
+    // grid: one CTA per 256 KB of the largest per-peer block, at least 1, at most the SM count
+    long long grid = (max_peer_bytes + (256ll << 10) - 1) / (256ll << 10);
+    const int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    a2a_push_kernel<<<(unsigned)grid, kA2AThreads, 0, st>>>(a, unit_log2);
+    count_launch();
+    PB200_LAUNCH_CHECK();
+    return PB200_OK;
+}
+
+extern "C" int pb200_a2a_single(pb200_a2a_comm *c, const void *in, int64_t total_in_bytes,
+                                const int64_t *in_split_bytes, const int64_t *out_split_bytes,
+                                int64_t out_window_off, void *out, void *stream) {
+    if (!c || (!in && total_in_bytes > 0) || total_in_bytes < 0 || out_window_off < 0)
+        return PB200_EINVAL;
+    if ((in_split_bytes == nullptr) != (out_split_bytes == nullptr)) return PB200_EINVAL;
+    const int W = c->world;
+    if (!in_split_bytes && total_in_bytes % W != 0) return PB200_EINVAL;
+    A2AArgs a{};
+    long long in_off = 0, out_off = out_window_off, max_peer = 0, total_out = 0;
+    for (int r = 0; r < W; ++r) {
+        const long long sb = in_split_bytes ? in_split_bytes[r] : total_in_bytes / W;
+        const long long rb = out_split_bytes ? out_split_bytes[r] : total_in_bytes / W;
+        if (sb < 0 || rb < 0) return PB200_EINVAL;
+        a.copy[r].src = (const unsigned char *)in + in_off;
+        a.copy[r].src_stride = 0;
+        a.copy[r].dst_stride = 0;
+        a.copy[r].run_bytes = sb;
+        a.copy[r].rows = sb > 0 ? 1 : 0;
+        a.recv_off[r] = out_off;
+        in_off += sb;
+        out_off += rb;
+        total_out += rb;
+        if (sb > max_peer) max_peer = sb;
+    }
+    if (in_off != total_in_bytes && in_split_bytes) return PB200_EINVAL;
+    if (out_off > c->window_bytes) return PB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = a2a_launch(c, a, max_peer, st);
+    if (rc != PB200_OK) return rc;
+    if (out && total_out > 0)
+        PB200_CUDA_TRY(cudaMemcpyAsync(out, c->peer_data[c->rank] + out_window_off, (size_t)total_out,
+                                       cudaMemcpyDeviceToDevice, st));
+    return PB200_OK;
+}
+
+extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t in_stride_t,
+                                    int64_t in_stride_n, int32_t emb_dim,
+                                    const int64_t *batch_split, const int64_t *tables_split,
+                                    int64_t out_window_off, void *stream) {
+    if (!c || !in || !batch_split || !tables_split || emb_dim < 1 || out_window_off < 0)
+        return PB200_EINVAL;
+    const int W = c->world, me = c->rank;
+    long long T_global = 0, table_base[PB200_A2A_MAX_RANKS], n_base[PB200_A2A_MAX_RANKS], N = 0;
+    for (int r = 0; r < W; ++r) {
+        if (batch_split[r] < 0 || tables_split[r] < 0) return PB200_EINVAL;
+        table_base[r] = T_global;
+        T_global += tables_split[r];
+        n_base[r] = N;
+        N += batch_split[r];
+    }
+    const long long T_local = tables_split[me];
+    const long long E = emb_dim;
+    // the pushed run is one (row, table) cell of E floats unless the local layout already has the
+    // tables adjacent inside a row (in_stride_t == E), in which case it is the whole T_local*E run
+    const bool tables_adjacent = (in_stride_t == E) || T_local <= 1;
+    if (!tables_adjacent) {
+        // [T, N, E]-style input (dlrm.py torch.stack layout): one 2-D push per local table.
+        // Every rank must run the same number of rounds (epochs advance in lock step), so the
+        // round count is max_r tables_split[r]; ranks with fewer tables send empty rounds.
+        // (The TBE forward can write [N, T*E] directly, which is the single-launch fast path.)
+        cudaStream_t st = (cudaStream_t)stream;
+        long long T_max = 0;
+        for (int r = 0; r < W; ++r) T_max = tables_split[r] > T_max ? tables_split[r] : T_max;
+        if (out_window_off + batch_split[me] * T_global * E * 4 > c->window_bytes)
+            return PB200_EINVAL;
+        for (long long t = 0; t < T_max; ++t) {
+            A2AArgs a{};
+            long long max_peer = 0;
+            for (int j = 0; j < W; ++j) {
+                const bool have = t < T_local;
+                a.copy[j].src =
+                    (const unsigned char *)(in + (have ? t : 0) * in_stride_t + n_base[j] * in_stride_n);
+                a.copy[j].src_stride = in_stride_n * 4;
+                a.copy[j].dst_stride = T_global * E * 4;
+                a.copy[j].run_bytes = E * 4;
+                a.copy[j].rows = have ? batch_split[j] : 0;
+                // where source j's t-th table goes in MY window
+                a.recv_off[j] = out_window_off + (table_base[j] + t) * E * 4;
+                const long long bytes = E * 4 * a.copy[j].rows;
+                if (bytes > max_peer) max_peer = bytes;
+            }
+            int rc = a2a_launch(c, a, max_peer, st);
+            if (rc != PB200_OK) return rc;
+        }
+        return PB200_OK;
+    }
+    A2AArgs a{};
+    long long max_peer = 0;
+    for (int j = 0; j < W; ++j) {
+        a.copy[j].src = (const unsigned char *)(in + n_base[j] * in_stride_n);
+        a.copy[j].src_stride = in_stride_n * 4;
+        a.copy[j].dst_stride = T_global * E * 4;
+        a.copy[j].run_bytes = T_local * E * 4;
+        a.copy[j].rows = batch_split[j];
+        a.recv_off[j] = out_window_off + table_base[j] * E * 4;  // source j's columns in my rows
+        const long long bytes = a.copy[j].run_bytes * a.copy[j].rows;
+        if (bytes > max_peer) max_peer = bytes;
+    }
+    if (out_window_off + batch_split[me] * T_global * E * 4 > c->window_bytes) return PB200_EINVAL;
+    return a2a_launch(c, a, max_peer, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_a2a_pooled_bwd(pb200_a2a_comm *c, const float *grad, int32_t emb_dim,
+                                    const int64_t *batch_split, const int64_t *tables_split,
+                                    int64_t out_window_off, void *stream) {
+    if (!c || !grad || !batch_split || !tables_split || emb_dim < 1 || out_window_off < 0)
+        return PB200_EINVAL;
+    const int W = c->world, me = c->rank;
+    long long T_global = 0, table_base[PB200_A2A_MAX_RANKS], n_base[PB200_A2A_MAX_RANKS], N = 0;
+    for (int r = 0; r < W; ++r) {
+        if (batch_split[r] < 0 || tables_split[r] < 0) return PB200_EINVAL;
+        table_base[r] = T_global;
+        T_global += tables_split[r];
+        n_base[r] = N;
+        N += batch_split[r];
+    }
+    const long long E = emb_dim;
+    const long long T_local = tables_split[me];
+    // my grad [lN_me, T_global*E]: owner j gets columns [table_base[j]*E, +T_j*E) of every row,
+    // landing in its window as rows n_base[me] .. of a [N, T_j*E] tensor
+    A2AArgs a{};
+    long long max_peer = 0;
+    for (int j = 0; j < W; ++j) {
+        a.copy[j].src = (const unsigned char *)(grad + table_base[j] * E);
+        a.copy[j].src_stride = T_global * E * 4;
+        a.copy[j].dst_stride = tables_split[j] * E * 4;
+        a.copy[j].run_bytes = tables_split[j] * E * 4;
+        a.copy[j].rows = batch_split[me];
+        // source j's rows start at n_base[j] in MY [N, T_local*E] window tensor
+        a.recv_off[j] = out_window_off + n_base[j] * T_local * E * 4;
+        const long long bytes = a.copy[j].run_bytes * a.copy[j].rows;
+        if (bytes > max_peer) max_peer = bytes;
+    }
+    if (out_window_off + N * T_local * E * 4 > c->window_bytes) return PB200_EINVAL;
+    return a2a_launch(c, a, max_peer, (cudaStream_t)stream);
+}

@@ -1,0 +1,135 @@
+// common.cuh — shared device helpers for libparam_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/param_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libparam_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pb200 {
+
+// ---- launch accounting (pb200_launch_count) --------------------------------
+extern int64_t g_launch_count;
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (int64_t)n, __ATOMIC_RELAXED); }
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PB200_OK : (int)e; }
+#define PB200_CUDA_TRY(expr)                      \
+    do {                                          \
+        cudaError_t _e = (expr);                  \
+        if (_e != cudaSuccess) return (int)_e;    \
+    } while (0)
+#define PB200_LAUNCH_CHECK()                      \
+    do {                                          \
+        cudaError_t _e = cudaGetLastError();      \
+        if (_e != cudaSuccess) return (int)_e;    \
+    } while (0)
+
+int sm_count();  // cached, current device
+
+// ---- global-memory access with explicit cache policy -------------------------
+// Table rows: read-only path, allocate in L1 — under Zipf skew the hottest ~100
+// rows (51 KB at D=128) carry >50 % of the lookups and stay L1-resident.
+__device__ __forceinline__ float4 ld_row_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+// Streams read exactly once (indices, offsets, grad rows): do not pollute L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ long long ld_stream_i64(const long long *p) {
+    long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_i32(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// Output rows are written once and consumed by a later kernel: streaming store.
+__device__ __forceinline__ void st_stream_f4(float4 *p, const float4 &v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+// Vector reduction into global memory (sm_90+): one 16 B red per lane.
+__device__ __forceinline__ void red_add_f4(float4 *p, const float4 &v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <typename index_t>
+__device__ __forceinline__ long long ld_index(const index_t *p);
+template <>
+__device__ __forceinline__ long long ld_index<long long>(const long long *p) {
+    return ld_stream_i64(p);
+}
+template <>
+__device__ __forceinline__ long long ld_index<int>(const int *p) {
+    return (long long)ld_stream_i32(p);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA unit, SASS UBLKCP) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; src and dst 16 B aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- counter-based RNG (splitmix64 finaliser) -----------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace pb200

@@ -1,0 +1,281 @@
+"""Torch-tensor host layer over the C ABI (include/param_b200.h).
+
+PyTorch is used here for device memory, streams and dtype bookkeeping only: every function
+passes raw device pointers + the current CUDA stream to libparam_b200.so.  Nothing in this
+module computes on the CPU or falls back to ATen kernels; a non-CUDA tensor is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import (BWD_ATOMIC, BWD_AUTO, BWD_SORTED, FWD_AUTO, FWD_DIRECT, FWD_STAGED,  # noqa: F401
+                    IDX_I32, IDX_I64, POOL_MEAN, POOL_SUM, PB200Error)
+
+_MODE = {"sum": POOL_SUM, "mean": POOL_MEAN}
+_FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED}
+_BWD_ALGO = {"auto": BWD_AUTO, "atomic": BWD_ATOMIC, "sorted": BWD_SORTED}
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PB200Error(
+                "param_b200 kernels run on CUDA tensors only (no CPU fallback); got a "
+                f"{t.device} tensor"
+            )
+
+
+def _idx_type(indices: torch.Tensor, offsets: torch.Tensor) -> int:
+    if indices.dtype != offsets.dtype:
+        raise PB200Error("indices and offsets must have the same integer dtype")
+    if indices.dtype == torch.int64:
+        return IDX_I64
+    if indices.dtype == torch.int32:
+        return IDX_I32
+    raise PB200Error(f"unsupported index dtype {indices.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------
+# single-table EmbeddingBag forward (nn.EmbeddingBag call contract)
+# --------------------------------------------------------------------------------------
+def embedding_bag_forward(weight: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor,
+                          mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None,
+                          include_last_offset: bool = False, algo: str = "auto",
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = pool_{i in bag b} weight[indices[i]]  — reference call site
+    train/compute/pt/pytorch_emb.py:61 / train/comms/pt/dlrm.py:380."""
+    _need_cuda(weight, indices, offsets, per_sample_weights, out)
+    if weight.dtype != torch.float32 or weight.dim() != 2 or not weight.is_contiguous():
+        raise PB200Error("weight must be a contiguous fp32 [rows, dim] tensor")
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    n_bags = offsets.numel() - (1 if include_last_offset else 0)
+    if n_bags < 0:
+        raise PB200Error("include_last_offset requires at least one offset")
+    rows, dim = weight.shape
+    if out is None:
+        out = torch.empty((n_bags, dim), dtype=torch.float32, device=weight.device)
+    elif out.shape != (n_bags, dim) or out.dtype != torch.float32 or out.stride(1) != 1:
+        raise PB200Error("out must be fp32 [n_bags, dim] with unit inner stride")
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+        if psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must match indices")
+    rc = _cabi.load().pb200_embbag_fwd(
+        weight.data_ptr(), rows, dim, _ptr(indices), indices.numel(), _ptr(offsets), n_bags,
+        1 if include_last_offset else 0, it, _ptr(psw), _MODE[mode], out.data_ptr(),
+        out.stride(0) if n_bags > 0 else dim, _FWD_ALGO[algo], _stream_ptr(weight))
+    _cabi.check(rc, "pb200_embbag_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# batched multi-table (TBE layout)
+# --------------------------------------------------------------------------------------
+@dataclass
+class TableArena:
+    """T embedding tables in one fp32 arena [sum(rows), dim]; table t = rows
+    [row_offsets[t], row_offsets[t+1]).  Mirrors the storage of fbgemm's
+    SplitTableBatchedEmbeddingBagsCodegen (weights_offsets) that
+    train/comms/pt/comms_utils.py:1995-2017 constructs, with a uniform dim."""
+    weights: torch.Tensor            # fp32 [total_rows, dim], CUDA
+    row_offsets: torch.Tensor        # int64 [T+1], CUDA
+    rows: Sequence[int]              # host copy of per-table row counts
+    dim: int
+
+    @property
+    def num_tables(self) -> int:
+        return len(self.rows)
+
+    @property
+    def total_rows(self) -> int:
+        return int(self.weights.shape[0])
+
+    def table(self, t: int) -> torch.Tensor:
+        lo = sum(self.rows[:t])
+        return self.weights[lo:lo + self.rows[t]]
+
+    @staticmethod
+    def allocate(rows: Sequence[int], dim: int, device) -> "TableArena":
+        total = int(sum(rows))
+        if total >= 2 ** 32:
+            raise PB200Error("arena row count must stay below 2^32")
+        w = torch.empty((total, dim), dtype=torch.float32, device=device)
+        ro = torch.tensor([0] + list(torch.tensor(list(rows), dtype=torch.int64).cumsum(0).tolist()),
+                          dtype=torch.int64, device=device)
+        return TableArena(w, ro, list(int(r) for r in rows), int(dim))
+
+
+def tbe_forward(arena: TableArena, indices: torch.Tensor, offsets: torch.Tensor, batch: int,
+                mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None,
+                layout: str = "BTD", algo: str = "auto",
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched lookup over all tables of the arena.  offsets has T*batch + 1 entries (TBE request
+    layout, split_table_batched_embeddings_ops.py:93-135).  layout "BTD" -> out [batch, T*dim]
+    (TBE / all-to-all-ready), "TBD" -> out [T, batch, dim] (dlrm.py:387 torch.stack layout)."""
+    _need_cuda(arena.weights, indices, offsets, per_sample_weights, out)
+    T, D = arena.num_tables, arena.dim
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    if offsets.numel() != T * batch + 1:
+        raise PB200Error(f"offsets must have T*batch+1 = {T * batch + 1} entries, got {offsets.numel()}")
+    if layout == "BTD":
+        shape, st_t, st_b = (batch, T * D), D, T * D
+    elif layout == "TBD":
+        shape, st_t, st_b = (T, batch, D), batch * D, D
+    else:
+        raise PB200Error("layout must be 'BTD' or 'TBD'")
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=arena.weights.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype != torch.float32:
+        raise PB200Error(f"out must be contiguous fp32 {shape}")
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+    rc = _cabi.load().pb200_tbe_fwd(
+        arena.weights.data_ptr(), arena.row_offsets.data_ptr(), T, D, _ptr(indices),
+        indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode], out.data_ptr(),
+        st_t, st_b, _FWD_ALGO[algo], _stream_ptr(arena.weights))
+    _cabi.check(rc, "pb200_tbe_fwd")
+    return out
+
+
+_scratch_cache: dict = {}
+
+
+def _scratch(device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
+def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, dim: int,
+                 indices: torch.Tensor, offsets: torch.Tensor, batch: int,
+                 grad_out: torch.Tensor, layout: str = "BTD", scale: float = 1.0,
+                 mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None,
+                 algo: str = "auto") -> None:
+    """dst[row(t, idx[i])] += scale * w_i * grad_out[(t, bag(i))].  dst is either a dense grad
+    buffer shaped like the arena (scale=1) or the arena itself (scale=-lr, fused SGD).
+    Reference: autograd backward driven at pytorch_dist_backend.py:849-857 / dlrm.py:1296."""
+    _need_cuda(dst, row_offsets, indices, offsets, grad_out, per_sample_weights)
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    T, D = num_tables, dim
+    if offsets.numel() != T * batch + 1:
+        raise PB200Error("offsets must have T*batch+1 entries")
+    grad_out = grad_out.contiguous()
+    if grad_out.dtype != torch.float32 or grad_out.numel() != T * batch * D:
+        raise PB200Error("grad_out must be fp32 with T*batch*dim elements")
+    if layout == "BTD":
+        st_t, st_b = D, T * D
+    elif layout == "TBD":
+        st_t, st_b = batch * D, D
+    else:
+        raise PB200Error("layout must be 'BTD' or 'TBD'")
+    lib = _cabi.load()
+    a = _BWD_ALGO[algo]
+    scratch_ptr, scratch_bytes = None, 0
+    if a in (BWD_SORTED, BWD_AUTO):
+        scratch_bytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, dst.shape[0], BWD_SORTED))
+        scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+    rc = lib.pb200_tbe_bwd(dst.data_ptr(), row_offsets.data_ptr(), T, D, _ptr(indices),
+                           indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode],
+                           grad_out.data_ptr(), st_t, st_b, float(scale), a, scratch_ptr,
+                           scratch_bytes, _stream_ptr(dst))
+    _cabi.check(rc, "pb200_tbe_bwd")
+
+
+def check_indices(row_offsets: torch.Tensor, num_tables: int, indices: torch.Tensor,
+                  offsets: torch.Tensor, batch: int) -> int:
+    """Debug-mode bounds check; returns the number of out-of-range lookups (synchronises)."""
+    _need_cuda(row_offsets, indices, offsets)
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    bad = torch.zeros(1, dtype=torch.int64, device=indices.device)
+    rc = _cabi.load().pb200_check_indices(row_offsets.data_ptr(), num_tables, _ptr(indices),
+                                          indices.numel(), _ptr(offsets), batch,
+                                          _idx_type(indices, offsets), bad.data_ptr(),
+                                          _stream_ptr(indices))
+    _cabi.check(rc, "pb200_check_indices")
+    return int(bad.item())
+
+
+# --------------------------------------------------------------------------------------
+# sparse-input regroup (dlrm.py:430-504)
+# --------------------------------------------------------------------------------------
+def regroup_sparse(lengths: torch.Tensor, indices: torch.Tensor, world: int, tables_local: int,
+                   local_batch: int):
+    """lengths [W][T_l][b] + indices in the same order  ->  (lengths_out [T_l, W*b],
+    offsets_out [T_l*W*b+1], indices_out table-major).  int64, bit-exact."""
+    _need_cuda(lengths, indices)
+    lengths = lengths.contiguous().view(-1)
+    indices = indices.contiguous().view(-1)
+    if lengths.dtype != torch.int64 or indices.dtype != torch.int64:
+        raise PB200Error("regroup_sparse takes int64 lengths and indices")
+    n = world * tables_local * local_batch
+    if lengths.numel() != n:
+        raise PB200Error("lengths must have W*T_l*b elements")
+    dev = lengths.device
+    lengths_out = torch.empty(n, dtype=torch.int64, device=dev)
+    offsets_out = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    indices_out = torch.empty_like(indices)
+    lib = _cabi.load()
+    sb = int(lib.pb200_regroup_scratch_bytes(world, tables_local, local_batch))
+    scratch = _scratch(dev, sb)
+    rc = lib.pb200_regroup_sparse(lengths.data_ptr(), _ptr(indices), indices.numel(), world,
+                                  tables_local, local_batch, lengths_out.data_ptr(),
+                                  offsets_out.data_ptr(), _ptr(indices_out), scratch.data_ptr(),
+                                  sb, _stream_ptr(lengths))
+    _cabi.check(rc, "pb200_regroup_sparse")
+    return lengths_out.view(tables_local, world * local_batch), offsets_out, indices_out
+
+
+# --------------------------------------------------------------------------------------
+# synthetic data on the device
+# --------------------------------------------------------------------------------------
+def fill_uniform_(t: torch.Tensor, lo: float, hi: float, seed: int) -> torch.Tensor:
+    _need_cuda(t)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise PB200Error("fill_uniform_ takes a contiguous fp32 tensor")
+    rc = _cabi.load().pb200_fill_uniform(t.data_ptr(), t.numel(), float(lo), float(hi),
+                                         C.c_uint64(seed & (2 ** 64 - 1)), _stream_ptr(t))
+    _cabi.check(rc, "pb200_fill_uniform")
+    return t
+
+
+def fill_zipf_indices_(t: torch.Tensor, nnz: int, cdf: torch.Tensor, seed: int,
+                       dedupe: bool = True) -> torch.Tensor:
+    """t: int64 [n_bags * nnz]; bag-wise truncated-Zipf draws (distinct inside a bag if dedupe)."""
+    _need_cuda(t, cdf)
+    if t.dtype != torch.int64 or cdf.dtype != torch.float64 or not t.is_contiguous():
+        raise PB200Error("fill_zipf_indices_ takes a contiguous int64 destination and a float64 cdf")
+    if t.numel() % nnz != 0:
+        raise PB200Error("destination size must be a multiple of nnz")
+    rc = _cabi.load().pb200_fill_zipf_indices(t.data_ptr(), t.numel() // nnz, nnz, cdf.data_ptr(),
+                                              cdf.numel(), 1 if dedupe else 0,
+                                              C.c_uint64(seed & (2 ** 64 - 1)), _stream_ptr(t))
+    _cabi.check(rc, "pb200_fill_zipf_indices")
+    return t

@@ -1,0 +1,252 @@
+#!/usr/bin/env python3
+"""Generate the golden vectors that pin oracle/ against the REFERENCE's own code.
+
+Run in the build container only (it imports /root/reference, which does not exist on the GPU
+box):      python tests/golden/make_golden.py
+
+The reference holds no golden vectors / known-answer tests for this path, so the
+fixtures are produced by running the reference's own call sites here:
+
+  embbag_torch_cpu.npz  torch.nn.EmbeddingBag on CPU — the exact op the reference calls at
+                        train/compute/pt/pytorch_emb.py:179,40 and train/comms/pt/dlrm.py:379-380 —
+                        forward (sum / mean / per_sample_weights) and autograd dense backward.
+  init_indices_ref.npz  the reference's init_indices (train/compute/pt/pytorch_emb.py:138-160),
+                        imported from /root/reference, uniform and Zipf branches, seeded.
+  dlrm_sparse_ref.npz   the reference's calculateLengths / splitPerTable / lengthsToOffsets
+                        (train/comms/pt/dlrm.py:226-251, 430-504), imported from /root/reference.
+  a2a_gloo_ref.npz      3 gloo ranks: c10d all_to_all_single with uneven splits (the call at
+                        train/comms/pt/pytorch_dist_backend.py:336-351) and the reference's own
+                        All2Allv_Req / All2Allv_Wait autograd Functions + torch.cat
+                        (train/comms/pt/dlrm.py:86-218, 858-878, 1253), forward and backward.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+HERE = Path(__file__).resolve().parent
+REF = Path("/root/reference")
+
+
+def _ref_paths():
+    """Make `param_bench.train.comms.pt` and the script-dir imports of dlrm.py resolvable."""
+    alias_root = Path(tempfile.gettempdir()) / "pb200_ref_alias"
+    alias_root.mkdir(exist_ok=True)
+    link = alias_root / "param_bench"
+    if not link.exists():
+        link.symlink_to(REF)
+    sys.dont_write_bytecode = True
+    for p in (str(alias_root), str(REF / "train" / "comms" / "pt"), str(REF / "train" / "compute" / "pt")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+# ----------------------------------------------------------------------------------------------
+def gen_embbag():
+    rng = np.random.default_rng(20260925)
+    cases = []
+
+    def case(rows, dim, offsets, n_idx, mode="sum", weighted=False, idx=None):
+        if idx is None:
+            idx = rng.integers(0, rows, size=n_idx)
+        cases.append(dict(rows=rows, dim=dim, offsets=np.asarray(offsets, np.int64),
+                          indices=np.asarray(idx, np.int64), mode=mode, weighted=weighted))
+
+    # 0: empty bags, trailing bag runs to the end, duplicate indices inside a bag
+    case(37, 8, [0, 0, 3, 3, 7, 7], 11, idx=[5, 5, 9, 0, 36, 36, 36, 1, 2, 2, 30])
+    # 1: cfg1-like (dim 64, fixed bag 20)
+    case(1000, 64, np.arange(16) * 20, 320)
+    # 2: dataset B shape (dim 56, bag 34)
+    case(500, 56, np.arange(8) * 34, 272)
+    # 3: dim 128, mean pooling, ragged incl. one empty bag
+    case(300, 128, [0, 4, 4, 9, 30], 41, mode="mean")
+    # 4: per_sample_weights (sum mode), dim 12
+    case(64, 12, [0, 2, 5, 6], 9, weighted=True)
+    # 5: odd dim -> scalar path, bag size 1
+    case(40, 7, np.arange(10), 10)
+    # 6: dim 256 (two float4 chunks per lane), ragged, bag longer than 32
+    case(200, 256, [0, 40, 41, 41, 80], 97)
+    # 7: dim 4, tiny
+    case(10, 4, [0, 1, 3], 6)
+    # 8: all bags empty except the last
+    case(20, 16, [0, 0, 0, 0], 5)
+    # 9: dim 512 upper edge of the vector path
+    case(50, 512, [0, 3, 10], 12, mode="mean")
+
+    out = {"n_cases": np.int64(len(cases))}
+    for k, c in enumerate(cases):
+        torch.manual_seed(100 + k)
+        emb = nn.EmbeddingBag(c["rows"], c["dim"], mode=c["mode"])  # default N(0,1) init
+        idx = torch.from_numpy(c["indices"])
+        off = torch.from_numpy(c["offsets"])
+        psw = torch.rand(idx.numel()) + 0.5 if c["weighted"] else None
+        res = emb(idx, off, per_sample_weights=psw)
+        g = torch.randn_like(res)
+        res.backward(g)
+        p = f"c{k}_"
+        out[p + "weight"] = emb.weight.detach().numpy().copy()
+        out[p + "indices"] = c["indices"]
+        out[p + "offsets"] = c["offsets"]
+        out[p + "mode"] = np.array(c["mode"])
+        out[p + "psw"] = psw.numpy() if psw is not None else np.zeros(0, np.float32)
+        out[p + "out"] = res.detach().numpy().copy()
+        out[p + "grad_out"] = g.numpy().copy()
+        out[p + "grad_weight"] = emb.weight.grad.numpy().copy()
+    np.savez_compressed(HERE / "embbag_torch_cpu.npz", **out)
+    print("embbag_torch_cpu.npz:", len(cases), "cases")
+
+
+# ----------------------------------------------------------------------------------------------
+def gen_init_indices():
+    _ref_paths()
+    import pytorch_emb as ref_emb  # /root/reference/train/compute/pt/pytorch_emb.py
+
+    out = {}
+    torch.manual_seed(7)
+    out["uniform_seed"] = np.int64(7)
+    out["uniform_args"] = np.array([5000, 64, 6], np.int64)  # features, batch, nnz
+    out["uniform"] = ref_emb.init_indices(0.0, 5000, 64, 6).numpy()
+    np.random.seed(1234)
+    out["zipf_seed"] = np.int64(1234)
+    out["zipf_args"] = np.array([2000, 48, 5], np.int64)
+    out["zipf_alpha"] = np.float64(1.15)
+    out["zipf"] = ref_emb.init_indices(1.15, 2000, 48, 5).numpy()
+    np.savez_compressed(HERE / "init_indices_ref.npz", **out)
+    print("init_indices_ref.npz")
+
+
+# ----------------------------------------------------------------------------------------------
+def gen_dlrm_sparse():
+    _ref_paths()
+    import dlrm as ref_dlrm  # /root/reference/train/comms/pt/dlrm.py
+
+    rng = np.random.default_rng(99)
+    out = {}
+    # --- calculateLengths: per-feature offsets/indices -> flat lengths/indices (dlrm.py:226-242)
+    feat, b = 4, 5
+    offs, idxs = [], []
+    for f in range(feat):
+        lens = rng.integers(0, 4, size=b)
+        lens[rng.integers(0, b)] = 0
+        o = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        offs.append(torch.from_numpy(o))
+        idxs.append(torch.from_numpy(rng.integers(0, 100, size=int(lens.sum())).astype(np.int64)))
+    lengths, indices = ref_dlrm.calculateLengths(feat, offs, idxs)
+    out["cl_feat"], out["cl_batch"] = np.int64(feat), np.int64(b)
+    for f in range(feat):
+        out[f"cl_off{f}"] = offs[f].numpy()
+        out[f"cl_idx{f}"] = idxs[f].numpy()
+    out["cl_lengths"] = lengths.numpy()
+    out["cl_indices"] = indices.numpy()
+
+    # --- splitPerTable + lengthsToOffsets (dlrm.py:430-504, 245-251)
+    for name, (W, Tl, bb) in {"a": (3, 2, 4), "b": (2, 3, 5), "c": (4, 1, 3)}.items():
+        lens = rng.integers(0, 5, size=W * Tl * bb).astype(np.int64)
+        ind = rng.integers(0, 1000, size=int(lens.sum())).astype(np.int64)
+        offsets, indices_pt = ref_dlrm.paramDLRM_Net.splitPerTable(
+            None, torch.from_numpy(lens), torch.from_numpy(ind), bb, Tl, W, 0, torch.device("cpu"))
+        out[f"sp_{name}_dims"] = np.array([W, Tl, bb], np.int64)
+        out[f"sp_{name}_lengths"] = lens
+        out[f"sp_{name}_indices"] = ind
+        for f in range(Tl):
+            out[f"sp_{name}_off{f}"] = offsets[f].numpy().astype(np.int64)
+            out[f"sp_{name}_idx{f}"] = indices_pt[f].numpy().astype(np.int64)
+    np.savez_compressed(HERE / "dlrm_sparse_ref.npz", **out)
+    print("dlrm_sparse_ref.npz")
+
+
+# ----------------------------------------------------------------------------------------------
+W_A2A = 3
+A2A_SPLITS = [[1, 2, 3], [0, 4, 2], [5, 0, 1]]  # elements rank s sends to rank d
+POOL_N, POOL_E, POOL_TG = 7, 4, 5
+
+
+def _a2a_worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _ref_paths()
+    import dlrm as ref_dlrm
+
+    res = {}
+    # (a) raw c10d all_to_all_single, uneven splits, position-coded payloads
+    in_splits = A2A_SPLITS[rank]
+    out_splits = [A2A_SPLITS[s][rank] for s in range(world)]
+    for dt, tag in ((torch.int64, "i64"), (torch.float32, "f32")):
+        inp = (torch.arange(sum(in_splits)) + 1000 * rank).to(dt)
+        outp = torch.empty(sum(out_splits), dtype=dt)
+        dist.all_to_all_single(outp, inp, out_splits, in_splits)
+        res[f"raw_{tag}_in"] = inp.numpy()
+        res[f"raw_{tag}_out"] = outp.numpy()
+
+    # (b) the reference's pooled-embedding exchange: All2Allv_Req / All2Allv_Wait + cat
+    class StubBackend:
+        def sync_barrier(self, ca):
+            dist.barrier()
+
+        def complete_accel_ops(self, ca):
+            pass
+
+        def all_to_allv(self, ca, retFlag=False):
+            return dist.all_to_all_single(ca.opTensor, ca.ipTensor, ca.opTensor_split,
+                                          ca.ipTensor_split, async_op=True)
+
+    get_split = lambda n, r, w: ref_dlrm.paramDLRM_Net.get_split_lengths_by_len(None, n, r, w)  # noqa: E731
+    _, n_emb_per_rank = get_split(POOL_TG, rank, world)
+    bench = types.SimpleNamespace(
+        measured_regions={"fwd_a2a": {"memory": []}, "bwd_a2a": {"memory": []}},
+        commDetails=[], collectiveArgs=types.SimpleNamespace(timers={}),
+        backendFuncs=StubBackend(), my_size=world,
+        paramNN=types.SimpleNamespace(get_split_lengths_by_len=get_split))
+    bench.myreq = ref_dlrm.Request(bench)
+    T_l = n_emb_per_rank[rank]
+    g = torch.Generator().manual_seed(50 + rank)
+    ly = torch.randn(T_l, POOL_N, POOL_E, generator=g).requires_grad_()
+    dims_sum_per_rank = [t * POOL_E for t in n_emb_per_rank]
+    req = ref_dlrm.commsDLRMBench.alltoallv(bench, ly, rank, dims_sum_per_rank, n_emb_per_rank)
+    B = req.wait()
+    tempB = torch.cat(B, dim=1)
+    C = torch.randn(tempB.shape, generator=g)
+    tempB.backward(C)
+    res["pool_ly"] = ly.detach().numpy()
+    res["pool_out"] = tempB.detach().numpy()
+    res["pool_gradout"] = C.numpy()
+    res["pool_gradin"] = ly.grad.numpy()
+    res["pool_tables_split"] = np.array(n_emb_per_rank, np.int64)
+    lN, gNS = get_split(POOL_N, rank, world)
+    res["pool_batch_split"] = np.array(gNS, np.int64)
+    np.savez(os.path.join(tmpdir, f"rank{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_a2a():
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_a2a_worker, args=(W_A2A, 29611, td), nprocs=W_A2A, join=True)
+        out = {"world": np.int64(W_A2A), "splits": np.array(A2A_SPLITS, np.int64),
+               "pool_dims": np.array([POOL_N, POOL_E, POOL_TG], np.int64)}
+        for r in range(W_A2A):
+            d = np.load(os.path.join(td, f"rank{r}.npz"))
+            for k in d.files:
+                out[f"r{r}_{k}"] = d[k]
+    np.savez_compressed(HERE / "a2a_gloo_ref.npz", **out)
+    print("a2a_gloo_ref.npz")
+
+
+if __name__ == "__main__":
+    if not REF.exists():
+        raise SystemExit("/root/reference not present: golden vectors can only be regenerated "
+                         "in the build container")
+    gen_embbag()
+    gen_init_indices()
+    gen_dlrm_sparse()
+    gen_a2a()

@@ -1,0 +1,55 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/param_b200.h
+declares (no compute calls here).  Also: the product package never touches oracle/."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    text = (ROOT / "include" / "param_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from param_b200 import build, _cabi
+    lib_path = build.build_cuda()
+    assert lib_path.exists()
+    declared = _declared()
+    assert len(declared) >= 20
+    assert sorted(_cabi.EXPORTED_SYMBOLS) == declared
+    lib = ctypes.CDLL(str(lib_path))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in param_b200.h but not exported"
+
+
+def test_abi_loads_and_reports_errors_without_gpu():
+    from param_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.pb200_abi_version() == 1
+    assert b"invalid" in lib.pb200_error_string(-1)
+    assert lib.pb200_launch_count() >= 0
+    # argument validation happens before any CUDA call
+    assert lib.pb200_embbag_fwd(None, 0, 4, None, 0, None, 0, 0, 0, None, 0, None, 4, 0, None) == -1
+
+
+def test_product_package_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[./]|libparam_oracle", re.M)
+    for py in (ROOT / "param_b200").rglob("*.py"):
+        if py.name == "build.py":   # build() compiles the checker; it does not use it
+            continue
+        assert not pat.search(py.read_text()), f"{py} references oracle/"
+    for src in (ROOT / "param_b200" / "csrc").glob("*"):
+        assert "oracle" not in src.read_text().lower(), f"{src} references the oracle"
+
+
+def test_kernels_refuse_cpu_tensors():
+    import pytest
+    import torch
+    from param_b200 import ops
+    from param_b200._cabi import PB200Error
+    with pytest.raises(PB200Error):
+        ops.embedding_bag_forward(torch.randn(4, 4), torch.zeros(2, dtype=torch.int64),
+                                  torch.zeros(2, dtype=torch.int64))

@@ -1,0 +1,111 @@
+"""Pin the CPU oracle against the golden vectors generated from the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+
+def _cases(golden_dir):
+    d = np.load(golden_dir / "embbag_torch_cpu.npz")
+    for k in range(int(d["n_cases"])):
+        p = f"c{k}_"
+        psw = d[p + "psw"]
+        yield k, dict(weight=d[p + "weight"], indices=d[p + "indices"], offsets=d[p + "offsets"],
+                      mode=str(d[p + "mode"]), psw=psw if psw.size else None, out=d[p + "out"],
+                      grad_out=d[p + "grad_out"], grad_weight=d[p + "grad_weight"])
+
+
+def test_embbag_forward_matches_torch_cpu(oracle, golden_dir):
+    for k, c in _cases(golden_dir):
+        got = oracle.embbag_fwd(c["weight"], c["indices"], c["offsets"], mode=c["mode"], psw=c["psw"])
+        if c["mode"] == "sum" and c["psw"] is None:
+            # sequential in-order fp32 accumulation == torch CPU bit for bit
+            assert np.array_equal(got, c["out"]), f"case {k}"
+        else:
+            np.testing.assert_allclose(got, c["out"], rtol=1e-6, atol=1e-6, err_msg=f"case {k}")
+
+
+def test_embbag_backward_matches_torch_autograd(oracle, golden_dir):
+    for k, c in _cases(golden_dir):
+        rows, dim = c["weight"].shape
+        got = oracle.embbag_bwd(rows, dim, c["indices"], c["offsets"], c["grad_out"],
+                                mode=c["mode"], psw=c["psw"])
+        np.testing.assert_allclose(got, c["grad_weight"], rtol=1e-5, atol=1e-5, err_msg=f"case {k}")
+        got64 = oracle.embbag_bwd(rows, dim, c["indices"], c["offsets"], c["grad_out"],
+                                  mode=c["mode"], psw=c["psw"], dtype=np.float64)
+        np.testing.assert_allclose(got64, c["grad_weight"], rtol=1e-5, atol=1e-5)
+
+
+def test_tbe_layout_is_per_table_loop(oracle, golden_dir):
+    """TBE request layout (split_table_batched_embeddings_ops.py:93-135): concatenated indices,
+    cumulative offsets; equals the per-table golden outputs."""
+    cs = [c for _, c in _cases(golden_dir) if c["weight"].shape[1] == 64 or c["weight"].shape[1] == 56]
+    # build a 2-table request out of two single-table goldens with equal batch? dims differ, so
+    # instead replicate case 1 (dim 64) as three tables with permuted indices
+    c = [c for _, c in _cases(golden_dir)][1]
+    W = c["weight"]
+    rows, dim = W.shape
+    B = c["offsets"].size
+    L = c["indices"].size // B
+    rng = np.random.default_rng(0)
+    tables = [W, W[::-1].copy(), W * 2.0]
+    idx = [c["indices"], rng.permutation(c["indices"]), c["indices"][::-1].copy()]
+    arena = np.concatenate(tables)
+    tro = np.array([0, rows, 2 * rows, 3 * rows], np.int64)
+    offsets = np.arange(3 * B + 1, dtype=np.int64) * L
+    out = oracle.tbe_fwd(arena, tro, dim, np.concatenate(idx), offsets, B, layout="BTD")
+    out_t = oracle.tbe_fwd(arena, tro, dim, np.concatenate(idx), offsets, B, layout="TBD")
+    for t in range(3):
+        ref = oracle.embbag_fwd(tables[t], idx[t], np.arange(B, dtype=np.int64) * L)
+        assert np.array_equal(out[:, t * dim:(t + 1) * dim], ref)
+        assert np.array_equal(out_t[t], ref)
+    assert np.array_equal(out[:, :dim], c["out"])
+
+
+def test_split_per_table_matches_reference(oracle, golden_dir):
+    d = np.load(golden_dir / "dlrm_sparse_ref.npz")
+    for name in "abc":
+        W, Tl, b = (int(x) for x in d[f"sp_{name}_dims"])
+        lens, ind = d[f"sp_{name}_lengths"], d[f"sp_{name}_indices"]
+        lengths_out, offsets_out, indices_out = oracle.split_per_table(lens, ind, W, Tl, b)
+        for f in range(Tl):
+            lo, hi = offsets_out[f * W * b], offsets_out[(f + 1) * W * b]
+            per_table_off = offsets_out[f * W * b:(f + 1) * W * b] - lo
+            assert np.array_equal(per_table_off, d[f"sp_{name}_off{f}"]), (name, f)
+            assert np.array_equal(indices_out[lo:hi], d[f"sp_{name}_idx{f}"]), (name, f)
+        assert offsets_out[-1] == ind.size
+
+
+def test_calculate_lengths_matches_reference(oracle, golden_dir):
+    d = np.load(golden_dir / "dlrm_sparse_ref.npz")
+    feat = int(d["cl_feat"])
+    got_l, got_i = [], []
+    for f in range(feat):
+        got_l.append(oracle.calculate_lengths(d[f"cl_off{f}"], d[f"cl_idx{f}"].size))
+        got_i.append(d[f"cl_idx{f}"])
+    assert np.array_equal(np.concatenate(got_l), d["cl_lengths"])
+    assert np.array_equal(np.concatenate(got_i), d["cl_indices"])
+
+
+def test_all_to_all_single_matches_c10d_gloo(oracle, golden_dir):
+    d = np.load(golden_dir / "a2a_gloo_ref.npz")
+    W = int(d["world"])
+    splits = d["splits"]
+    for tag in ("i64", "f32"):
+        ins = [d[f"r{r}_raw_{tag}_in"] for r in range(W)]
+        outs = oracle.all_to_all_single(ins, splits)
+        for r in range(W):
+            assert np.array_equal(outs[r], d[f"r{r}_raw_{tag}_out"]), (tag, r)
+
+
+def test_pooled_exchange_matches_reference_autograd_functions(oracle, golden_dir):
+    d = np.load(golden_dir / "a2a_gloo_ref.npz")
+    W = int(d["world"])
+    N, E, Tg = (int(x) for x in d["pool_dims"])
+    ts, bs = d["r0_pool_tables_split"], d["r0_pool_batch_split"]
+    assert int(ts.sum()) == Tg and int(bs.sum()) == N
+    outs = oracle.pooled_a2a_fwd([d[f"r{r}_pool_ly"] for r in range(W)], bs, ts, E)
+    for r in range(W):
+        assert np.array_equal(outs[r], d[f"r{r}_pool_out"]), r
+    gins = oracle.pooled_a2a_bwd([d[f"r{r}_pool_gradout"] for r in range(W)], bs, ts, E)
+    for r in range(W):
+        assert np.array_equal(gins[r], d[f"r{r}_pool_gradin"]), r
