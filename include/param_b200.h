@@ -176,6 +176,12 @@ int pb200_a2a_comm_create(pb200_a2a_comm **comm, int32_t rank, int32_t world,
                           void *const *peer_data, void *const *peer_signal,
                           int64_t window_bytes);
 int pb200_a2a_comm_destroy(pb200_a2a_comm *comm);
+/* max_ctas: cap on the grid of the push kernel (0 = SM count; < 0 leaves it unchanged);
+ * spin_timeout_s: a flag wait that lasts longer (a peer that never arrives) records an error
+ * instead of hanging the GPU (<= 0 leaves the ~10 s default). */
+int pb200_a2a_comm_config(pb200_a2a_comm *comm, int32_t max_ctas, double spin_timeout_s);
+/* Synchronous: *error_out != 0 if any collective on this communicator timed out. */
+int pb200_a2a_comm_error(pb200_a2a_comm *comm, int32_t *error_out);
 
 /* Byte-granular all_to_all_single.  `in` is any local device buffer (it need
  * not be in the window).  The result lands in THIS rank's data window at byte

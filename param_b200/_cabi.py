@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = (
     "pb200_abi_version", "pb200_error_string", "pb200_launch_count", "pb200_device_info",
     "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_check_indices",
     "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd",
-    "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_single",
+    "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
+    "pb200_a2a_comm_error", "pb200_a2a_single",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd",
     "pb200_regroup_scratch_bytes", "pb200_regroup_sparse",
     "pb200_host_ctx_create", "pb200_host_ctx_destroy", "pb200_tbe_fwd_host", "pb200_tbe_step_host",
@@ -79,6 +80,8 @@ def load():
         f32, i32, vp, i64, vp)
     sig("pb200_a2a_comm_create", C.c_int, C.POINTER(vp), i32, i32, C.POINTER(vp), C.POINTER(vp), i64)
     sig("pb200_a2a_comm_destroy", C.c_int, vp)
+    sig("pb200_a2a_comm_config", C.c_int, vp, i32, C.c_double)
+    sig("pb200_a2a_comm_error", C.c_int, vp, C.POINTER(i32))
     sig("pb200_a2a_single", C.c_int, vp, vp, i64, p_i64, p_i64, i64, vp, vp)
     sig("pb200_a2a_pooled_fwd", C.c_int, vp, vp, i64, i64, i32, p_i64, p_i64, i64, vp)
     sig("pb200_a2a_pooled_bwd", C.c_int, vp, vp, i32, p_i64, p_i64, i64, vp)

@@ -1,0 +1,302 @@
+"""DLRM communication pattern on the B200 kernels (mirror of train/comms/pt/dlrm.py).
+
+Table-parallel embeddings + batch-parallel dense part, joined by an all-to-all:
+
+  reference step (dlrm.py:1200-1323)                     here
+  ------------------------------------------------------ ------------------------------------------
+  SparseFeatures/calculateLengths (:226-277)             SparseBatch (lengths kept on the device)
+  SparseDataDist: lengths a2a, .item() sync, indices     sparse_data_dist(): peer-push a2a of lengths,
+    a2a, python splitPerTable (:744-855, :430-504)         ONE [W]-count D2H, peer-push a2a of indices,
+                                                            pb200_regroup_sparse (device)
+  apply_emb: T_l nn.EmbeddingBag launches + stack (:363) one batched TBE launch writing [N, T_l*E]
+  All2Allv_Req/Wait + 2 torch.cat (:86-218, :1253)       pb200_a2a_pooled_fwd: pooled rows pushed straight
+                                                            into the peers' final [lN, T_g*E] tensors
+  tempB.backward(C) -> a2a bwd + cat/split +             pb200_a2a_pooled_bwd + pb200_tbe_bwd scatter-add
+    EmbeddingBagBackward (:1296, :180-218, :137-154)
+  MLP-gradient all_reduce (:1266-1281, :1303-1317)       stays on NCCL (dist.all_reduce), out of scope
+
+Run:  torchrun --nproc-per-node 8 -m param_b200.comms.pt.dlrm --mini-batch-size 8192 \
+          --arch-embedding-size 1000000x512 --arch-sparse-feature-size 128 --num-indices-per-lookup 20
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from ... import ops
+from ..._cabi import PB200Error
+from .peer_window import PeerWindow
+
+
+def split_lengths(n: int, world: int) -> List[int]:
+    """Contiguous block split with the remainder on the low ranks (get_split_lengths_by_len,
+    dlrm.py:390-398)."""
+    k, m = divmod(int(n), int(world))
+    return [k + 1 if r < m else k for r in range(world)]
+
+
+def owner_slice(rank: int, split: Sequence[int]) -> slice:
+    """Tables owned by `rank` (get_slice_sparse, dlrm.py:424-428)."""
+    lo = sum(split[:rank])
+    return slice(lo, lo + split[rank])
+
+
+def parse_embedding_sizes(spec: str) -> List[int]:
+    """'1000-1000-2000' (reference syntax, dlrm.py:509) or the shorthand '1000000x512'."""
+    if "x" in spec:
+        rows, count = spec.split("x")
+        return [int(rows)] * int(count)
+    return [int(v) for v in spec.split("-") if v]
+
+
+@dataclass
+class SparseBatch:
+    """One rank's sparse inputs for its LOCAL batch and ALL global tables (table-major), the
+    interface SparseDataDist expects (dlrm.py:254-277)."""
+    count: int                 # T_global
+    batch_size: int            # local batch b
+    lengths: torch.Tensor      # int64 [T_global * b]
+    indices: torch.Tensor      # int64 [sum(lengths)], table-major then sample order
+
+    @staticmethod
+    def from_offsets(offsets: Sequence[torch.Tensor], indices: Sequence[torch.Tensor], device) -> "SparseBatch":
+        """Per-table nn.EmbeddingBag offsets/indices -> lengths (calculateLengths, dlrm.py:226-242:
+        first differences with the last bag closed by len(indices))."""
+        lens = []
+        for off, idx in zip(offsets, indices):
+            off = off.to(device=device, dtype=torch.int64)
+            end = torch.tensor([idx.numel()], dtype=torch.int64, device=device)
+            lens.append(torch.diff(torch.cat([off, end])))
+        b = offsets[0].numel()
+        return SparseBatch(len(offsets), b, torch.cat(lens),
+                           torch.cat([i.to(device=device, dtype=torch.int64) for i in indices]))
+
+    @staticmethod
+    def synthetic(table_rows: Sequence[int], local_batch: int, bag: int, fixed: bool, seed: int,
+                  device, alpha: float = 0.0) -> "SparseBatch":
+        """Device-side generator.  fixed bag size (reference --num-indices-per-lookup-fixed) or ragged
+        lengths uniform in [1, bag]; indices uniform (reference dlrm_data.py:182-183) or Zipf."""
+        from ...compute.pt.pytorch_emb import zipf_cdf
+        T, b = len(table_rows), int(local_batch)
+        g = torch.Generator(device=device)
+        g.manual_seed(int(seed))
+        if fixed:
+            lengths = torch.full((T * b,), int(bag), dtype=torch.int64, device=device)
+        else:
+            lengths = torch.randint(1, int(bag) + 1, (T * b,), generator=g, device=device, dtype=torch.int64)
+        per_table = lengths.view(T, b).sum(dim=1).tolist()
+        chunks, cdf_cache = [], {}
+        for t, rows in enumerate(table_rows):
+            n = int(per_table[t])
+            if alpha > 0:
+                if rows not in cdf_cache:
+                    cdf_cache[rows] = torch.from_numpy(zipf_cdf(alpha, rows)).to(device)
+                buf = torch.empty(n, dtype=torch.int64, device=device)
+                ops.fill_zipf_indices_(buf, 1, cdf_cache[rows], seed * 1315423911 + t, dedupe=False)
+                chunks.append(buf)
+            else:
+                chunks.append(torch.randint(0, int(rows), (n,), generator=g, device=device, dtype=torch.int64))
+        return SparseBatch(T, b, lengths, torch.cat(chunks) if chunks else lengths.new_empty(0))
+
+
+class DLRMParallelEmbedding:
+    """The table-parallel half of one DLRM iteration on one rank."""
+
+    def __init__(self, group, table_rows: Sequence[int], emb_dim: int, local_batch: int,
+                 max_bag: int, device: torch.device, lr: float = 0.0, seed: int = 0,
+                 window: Optional[PeerWindow] = None, bwd_algo: str = "atomic"):
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.table_rows = [int(r) for r in table_rows]
+        self.T_global, self.E = len(self.table_rows), int(emb_dim)
+        if self.T_global < self.world:
+            raise PB200Error("need at least one table per rank (dlrm.py:511-514)")
+        self.tables_split = split_lengths(self.T_global, self.world)
+        self.batch_split = [int(local_batch)] * self.world       # a2ai.gNS: equal local batches
+        self.b, self.N = int(local_batch), int(local_batch) * self.world
+        self.my_tables = owner_slice(self.rank, self.tables_split)
+        self.T_local = self.tables_split[self.rank]
+        self.lr, self.bwd_algo = float(lr), bwd_algo
+        rows = self.table_rows[self.my_tables]
+        self.arena = ops.TableArena.allocate(rows, self.E, device)
+        for t, n in enumerate(rows):  # U(+-sqrt(1/n)) init, alloc_embedding_tables pytorch_dist_backend.py:926-928
+            ops.fill_uniform_(self.arena.table(t), -(1.0 / n) ** 0.5, (1.0 / n) ** 0.5,
+                              seed=seed * 7919 + self.my_tables.start + t)
+        # window carve-up (identical on every rank: sized with the max over ranks)
+        T_max = max(self.tables_split)
+        self.cap_lengths = self.world * T_max * self.b
+        self.cap_indices = self.cap_lengths * int(max_bag)
+        need = (self.cap_lengths + self.cap_indices) * 8 + self.b * self.T_global * self.E * 4 \
+            + self.N * T_max * self.E * 4 + 4 * 512
+        self.window = window or PeerWindow.create(group, need, device)
+        if self.window.window_bytes < need:
+            raise PB200Error(f"window too small: {self.window.window_bytes} < {need}")
+        self.window.reset_alloc()
+        _, self.off_lengths = self.window.alloc(self.cap_lengths, torch.int64)
+        _, self.off_indices = self.window.alloc(self.cap_indices, torch.int64)
+        _, self.off_pooled = self.window.alloc(self.b * self.T_global * self.E, torch.float32)
+        _, self.off_grad = self.window.alloc(self.N * T_max * self.E, torch.float32)
+        self._pooled_local = torch.empty((self.N, self.T_local * self.E), dtype=torch.float32, device=device)
+        self._saved = None
+
+    # ---- step 2: SparseDataDist ---------------------------------------------------------------
+    def sparse_data_dist(self, batch: SparseBatch):
+        """batch-parallel -> table-parallel redistribution of (lengths, indices); returns the TBE
+        request (offsets int64[T_l*N+1], indices) for this rank's tables over the GLOBAL batch."""
+        W, b, win = self.world, self.b, self.window
+        if batch.count != self.T_global or batch.batch_size != b:
+            raise PB200Error("SparseBatch does not match the configured tables / local batch")
+        # lengths: in-splits T_r*b per destination, out-splits T_l*b per source (dlrm.py:768-785)
+        in_splits = [t * b for t in self.tables_split]
+        out_splits = [self.T_local * b] * W
+        lengths_out = win.all_to_all_single(None, batch.lengths, out_splits, in_splits,
+                                            out_window_off=self.off_lengths)
+        # element counts per destination / per source: the one host round trip (the reference has
+        # .item() + two .numpy() here, dlrm.py:801-818)
+        per_table = batch.lengths.view(self.T_global, b).sum(dim=1)
+        bounds = torch.tensor([0] + list(torch.tensor(self.tables_split).cumsum(0).tolist()), device=self.device)
+        csum = torch.cat([per_table.new_zeros(1), per_table.cumsum(0)])
+        send_counts = (csum[bounds[1:]] - csum[bounds[:-1]])
+        recv_counts = lengths_out.view(W, -1).sum(dim=1)
+        counts = torch.stack([send_counts, recv_counts]).cpu()
+        idx_in, idx_out = counts[0].tolist(), counts[1].tolist()
+        n_recv = int(sum(idx_out))
+        if n_recv > self.cap_indices:
+            raise PB200Error("received more indices than the window was sized for (raise max_bag)")
+        indices_out = win.all_to_all_single(None, batch.indices, idx_out, idx_in,
+                                            out_window_off=self.off_indices)
+        # per-table regroup + offsets (splitPerTable / lengthsToOffsets, dlrm.py:430-504, 245-251)
+        _, offsets, indices = ops.regroup_sparse(lengths_out, indices_out[:n_recv], W, self.T_local, b)
+        return offsets, indices
+
+    # ---- steps 3+4: apply_emb + forward all-to-all ------------------------------------------------
+    def forward(self, offsets: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+        """lookup for the global batch, then the fused exchange; returns [lN, T_global*E]."""
+        ops.tbe_forward(self.arena, indices, offsets, self.N, layout="BTD", out=self._pooled_local)
+        self._saved = (offsets, indices)
+        return self.window.pooled_forward(self._pooled_local, self.batch_split, self.tables_split, self.E,
+                                          layout="BTD", out_window_off=self.off_pooled)
+
+    # ---- step 6: backward all-to-all + scatter-add ---------------------------------------------------
+    def backward(self, grad: torch.Tensor) -> None:
+        offsets, indices = self._saved
+        g_local = self.window.pooled_backward(grad.contiguous(), self.batch_split, self.tables_split,
+                                              self.E, out_window_off=self.off_grad)
+        ops.tbe_backward(self.arena.weights, self.arena.row_offsets, self.T_local, self.E, indices,
+                         offsets, self.N, g_local, layout="BTD", scale=-self.lr, algo=self.bwd_algo)
+
+
+class NCCLReferenceEmbedding:
+    """Comparator: the same step the way the reference does it on the same box — per-table
+    torch.nn.EmbeddingBag, torch.stack, cat + dist.all_to_all_single (NCCL) + split/cat
+    (dlrm.py:363-388, 86-218, 1253).  Used only to print a baseline beside the B200 numbers."""
+
+    def __init__(self, group, peer: DLRMParallelEmbedding):
+        self.group, self.p = group, peer
+        import torch.nn as nn
+        self.embs = []
+        for t in range(peer.T_local):
+            e = nn.EmbeddingBag(peer.arena.rows[t], peer.E, mode="sum", sparse=True,
+                                _weight=peer.arena.table(t).clone())
+            self.embs.append(e.to(peer.device))
+
+    def forward(self, offsets, indices):
+        p = self.p
+        N, E, W = p.N, p.E, p.world
+        ly = []
+        for t, e in enumerate(self.embs):
+            lo, hi = offsets[t * N], offsets[(t + 1) * N]
+            ly.append(e(indices[lo:hi], offsets[t * N:(t + 1) * N] - lo))
+        ly = torch.stack(ly)                                            # [T_l, N, E]
+        inp = torch.cat(list(ly), dim=1).view(-1)                       # [N, T_l*E] flattened
+        in_splits = [m * p.T_local * E for m in p.batch_split]
+        out_splits = [p.b * t * E for t in p.tables_split]
+        out = inp.new_empty(sum(out_splits))
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
+        parts = [o.view(p.b, -1) for o in out.split(out_splits)]
+        return torch.cat(parts, dim=1)                                  # [lN, T_g*E]
+
+
+# ------------------------------------------------------------------------------------------------
+# runner
+# ------------------------------------------------------------------------------------------------
+def _parse(argv=None):
+    ap = argparse.ArgumentParser(description="DLRM comm pattern on B200 peer-push all-to-all")
+    ap.add_argument("--mini-batch-size", type=int, default=8192, help="per-rank batch")
+    ap.add_argument("--num-batches", type=int, default=10)
+    ap.add_argument("--warmup-batches", type=int, default=3)
+    ap.add_argument("--arch-embedding-size", type=str, default="100000x16")
+    ap.add_argument("--arch-sparse-feature-size", type=int, default=128)
+    ap.add_argument("--num-indices-per-lookup", type=int, default=20)
+    ap.add_argument("--num-indices-per-lookup-fixed", type=lambda s: str(s).lower() in ("1", "true"), default=True)
+    ap.add_argument("--alpha", type=float, default=0.0)
+    ap.add_argument("--lr", type=float, default=0.0)
+    ap.add_argument("--compare-nccl", action="store_true")
+    ap.add_argument("--json", action="store_true")
+    return ap.parse_args(argv)
+
+
+def run(argv=None):
+    args = _parse(argv)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    group = dist.group.WORLD
+    rows = parse_embedding_sizes(args.arch_embedding_size)
+    E, b, L = args.arch_sparse_feature_size, args.mini_batch_size, args.num_indices_per_lookup
+    model = DLRMParallelEmbedding(group, rows, E, b, L, dev, lr=args.lr, seed=1)
+    regions = ["offset_idx_xchg", "emb_lookup_fwd_a2a", "bwd_a2a_emb_update", "iter_time"]
+    samples = {k: [] for k in regions}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    grad = None
+    for it in range(args.warmup_batches + args.num_batches):
+        batch = SparseBatch.synthetic(rows, b, L, args.num_indices_per_lookup_fixed, seed=rank * 1000 + it,
+                                      device=dev, alpha=args.alpha)
+        dist.barrier(group)
+        torch.cuda.synchronize()
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        offsets, indices = model.sparse_data_dist(batch)
+        e[1].record()
+        out = model.forward(offsets, indices)
+        e[2].record()
+        if grad is None:
+            grad = torch.ones_like(out)
+        model.backward(grad)
+        e[3].record()
+        torch.cuda.synchronize()
+        if it >= args.warmup_batches:
+            samples["offset_idx_xchg"].append(e[0].elapsed_time(e[1]))
+            samples["emb_lookup_fwd_a2a"].append(e[1].elapsed_time(e[2]))
+            samples["bwd_a2a_emb_update"].append(e[2].elapsed_time(e[3]))
+            samples["iter_time"].append(e[0].elapsed_time(e[3]))
+    if model.window.error():
+        raise PB200Error("a peer wait timed out during the run")
+    stats = {}
+    for k, v in samples.items():
+        t = torch.tensor(v, device=dev).median().view(1)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        stats[k + "_ms_p50_max_rank"] = float(t.item())
+    if rank == 0:
+        if args.json:
+            print(json.dumps(stats))
+        else:
+            for k, v in stats.items():
+                print(f"{k:40s} {v:10.3f} ms")
+    dist.barrier(group)
+    return stats
+
+
+if __name__ == "__main__":
+    run()
+    if dist.is_initialized():
+        dist.destroy_process_group()

@@ -56,6 +56,8 @@ struct A2AArgs {
     unsigned long long *epoch;                      // device: last completed epoch
     unsigned *peer_cnt;                             // device [W]: CTAs finished per destination
     unsigned *grid_cnt;                             // device: CTAs finished overall
+    unsigned *error;                                // device: set to 1 when a spin wait timed out
+    long long spin_cycles;                          // give up a flag wait after this many clocks
     int rank;
     int world;
 };
@@ -87,6 +89,20 @@ __device__ __forceinline__ void st_peer_v4(int4 *p, const int4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                  "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
+}
+
+// Bounded spin on a flag in local memory: a peer that never arrives (crashed rank, mismatched
+// call sequence) must not hang the GPU — after spin_cycles the kernel records an error and moves on.
+__device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, unsigned long long e,
+                                             long long budget, unsigned *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < e) {
+        if (clock64() - t0 > budget) {
+            atomicExch(err, 1u);
+            return false;
+        }
+    }
+    return true;
 }
 
 constexpr int kA2AThreads = 512;
@@ -164,14 +180,14 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, 
             dst_off = a.recv_off[me];
         } else {
             if (threadIdx.x == 0) {
-                while (ld_acquire_sys(&my_pad->ready_epoch[j]) < e) {
-                }
-                s_payload = ld_relaxed_sys(&my_pad->ready_payload[j]);
+                const bool ok = wait_flag_ge(&my_pad->ready_epoch[j], e, a.spin_cycles, a.error);
+                // on timeout: skip this destination (payload -1), never write to an unready peer
+                s_payload = ok ? ld_relaxed_sys(&my_pad->ready_payload[j]) : ~0ull;
             }
             __syncthreads();
             dst_off = (long long)s_payload;
         }
-        if (total_units > 0) {
+        if (total_units > 0 && dst_off >= 0) {
             // contiguous slice of units per CTA (keeps each CTA's stores in long runs)
             const long long per = (total_units + gridDim.x - 1) / gridDim.x;
             const long long u0 = per * blockIdx.x;
@@ -209,8 +225,7 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, 
         if (prev == gridDim.x - 1) {
             for (int r = 0; r < W; ++r) {
                 if (r == me) continue;
-                while (ld_acquire_sys(&my_pad->done_epoch[r]) < e) {
-                }
+                wait_flag_ge(&my_pad->done_epoch[r], e, a.spin_cycles, a.error);
             }
             *a.grid_cnt = 0;
             *(volatile unsigned long long *)a.epoch = e;
@@ -232,6 +247,8 @@ struct pb200_a2a_comm {
     unsigned long long *d_epoch;
     unsigned *d_peer_cnt;
     unsigned *d_grid_cnt;
+    unsigned *d_error;
+    long long spin_cycles;
     int max_ctas;
 };
 
@@ -269,9 +286,26 @@ extern "C" int pb200_a2a_comm_create(pb200_a2a_comm **comm, int32_t rank, int32_
     c->d_epoch = (unsigned long long *)blk;
     c->d_grid_cnt = (unsigned *)(blk + 8);
     c->d_peer_cnt = (unsigned *)(blk + 64);
+    c->d_error = (unsigned *)(blk + 16);
+    c->spin_cycles = 20ll * 1000 * 1000 * 1000;  // ~10 s at 2 GHz
     const char *env = getenv("PB200_A2A_CTAS");
     c->max_ctas = env ? atoi(env) : 0;
     *comm = c;
+    return PB200_OK;
+}
+
+extern "C" int pb200_a2a_comm_config(pb200_a2a_comm *comm, int32_t max_ctas, double spin_timeout_s) {
+    if (!comm) return PB200_EINVAL;
+    if (max_ctas >= 0) comm->max_ctas = max_ctas;
+    if (spin_timeout_s > 0) comm->spin_cycles = (long long)(spin_timeout_s * 2.0e9);
+    return PB200_OK;
+}
+
+extern "C" int pb200_a2a_comm_error(pb200_a2a_comm *comm, int32_t *error_out) {
+    if (!comm || !error_out) return PB200_EINVAL;
+    unsigned v = 0;
+    PB200_CUDA_TRY(cudaMemcpy(&v, comm->d_error, sizeof(v), cudaMemcpyDeviceToHost));
+    *error_out = (int32_t)v;
     return PB200_OK;
 }
 
@@ -290,6 +324,8 @@ static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, c
     a.epoch = c->d_epoch;
     a.peer_cnt = c->d_peer_cnt;
     a.grid_cnt = c->d_grid_cnt;
+    a.error = c->d_error;
+    a.spin_cycles = c->spin_cycles;
     a.rank = c->rank;
     a.world = c->world;
     // common alignment of everything that moves -> copy unit

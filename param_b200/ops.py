@@ -76,6 +76,8 @@ def embedding_bag_forward(weight: torch.Tensor, indices: torch.Tensor, offsets: 
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
         if psw.numel() != indices.numel():
             raise PB200Error("per_sample_weights must match indices")
+    if n_bags == 0:
+        return out
     rc = _cabi.load().pb200_embbag_fwd(
         weight.data_ptr(), rows, dim, _ptr(indices), indices.numel(), _ptr(offsets), n_bags,
         1 if include_last_offset else 0, it, _ptr(psw), _MODE[mode], out.data_ptr(),
@@ -148,6 +150,8 @@ def tbe_forward(arena: TableArena, indices: torch.Tensor, offsets: torch.Tensor,
     psw = None
     if per_sample_weights is not None:
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+    if batch == 0:
+        return out
     rc = _cabi.load().pb200_tbe_fwd(
         arena.weights.data_ptr(), arena.row_offsets.data_ptr(), T, D, _ptr(indices),
         indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode], out.data_ptr(),

@@ -1,0 +1,136 @@
+"""The peer-push all-to-all protocol exercised on ONE GPU: W virtual ranks in one process, each
+with its own window, pad and stream (PeerWindow.local_group).  The kernels are the same ones that
+run across NVLink; only the pointers differ.  Golden vectors come from the reference's c10d/gloo
+run and its own All2Allv_Req/All2Allv_Wait Functions (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _group(W, window_bytes, dev):
+    from param_b200.comms.pt.peer_window import PeerWindow
+    return PeerWindow.local_group(W, window_bytes, dev, max_ctas=4, spin_timeout_s=5.0)
+
+
+def _run_all(grp, fn):
+    """launch fn(rank, window, stream) for every virtual rank, then synchronise and check errors"""
+    outs = []
+    for r, (w, st) in enumerate(zip(grp.windows, grp.streams)):
+        with torch.cuda.stream(st):
+            outs.append(fn(r, w, st))
+    torch.cuda.synchronize()
+    for w in grp.windows:
+        assert w.error() == 0, "a2a kernel timed out waiting for a peer"
+    return outs
+
+
+def test_all_to_all_single_matches_c10d_golden(cuda_device, golden_dir):
+    d = np.load(golden_dir / "a2a_gloo_ref.npz")
+    W = int(d["world"])
+    splits = d["splits"]
+    grp = _group(W, 1 << 16, cuda_device)
+    for tag, dt in (("i64", torch.int64), ("f32", torch.float32)):
+        ins = [torch.from_numpy(d[f"r{r}_raw_{tag}_in"]).to(cuda_device) for r in range(W)]
+        outs = [torch.empty(int(splits[:, r].sum()), dtype=dt, device=cuda_device) for r in range(W)]
+        _run_all(grp, lambda r, w, st: w.all_to_all_single(
+            outs[r], ins[r], [int(splits[s][r]) for s in range(W)], [int(x) for x in splits[r]], stream=st))
+        for r in range(W):
+            assert np.array_equal(outs[r].cpu().numpy(), d[f"r{r}_raw_{tag}_out"]), (tag, r)
+
+
+def test_pooled_exchange_matches_reference_functions(cuda_device, golden_dir):
+    d = np.load(golden_dir / "a2a_gloo_ref.npz")
+    W = int(d["world"])
+    N, E, Tg = (int(x) for x in d["pool_dims"])
+    ts = [int(x) for x in d["r0_pool_tables_split"]]
+    bs = [int(x) for x in d["r0_pool_batch_split"]]
+    grp = _group(W, 1 << 16, cuda_device)
+    for layout in ("TBD", "BTD"):
+        lys = []
+        for r in range(W):
+            ly = torch.from_numpy(d[f"r{r}_pool_ly"]).to(cuda_device)          # [T_r, N, E]
+            if layout == "BTD":
+                ly = ly.permute(1, 0, 2).contiguous().view(N, -1)              # [N, T_r*E]
+            lys.append(ly)
+        outs = _run_all(grp, lambda r, w, st: w.pooled_forward(lys[r], bs, ts, E, layout=layout, stream=st))
+        for r in range(W):
+            assert np.array_equal(outs[r].cpu().numpy(), d[f"r{r}_pool_out"]), (layout, r)
+    grads = [torch.from_numpy(d[f"r{r}_pool_gradout"]).to(cuda_device) for r in range(W)]
+    gins = _run_all(grp, lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, stream=st))
+    for r in range(W):
+        got = gins[r].view(N, ts[r], E).permute(1, 0, 2).cpu().numpy()          # -> [T_r, N, E]
+        assert np.array_equal(got, d[f"r{r}_pool_gradin"]), r
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int64, torch.uint8])
+def test_all_to_all_single_vs_oracle_repeated(cuda_device, oracle, W, dtype):
+    """position-coded payloads (a constant payload cannot detect a wrong permutation),
+    uneven splits incl. zero-length blocks, several epochs on the same communicator."""
+    rng = np.random.default_rng(W * 10 + dtype.itemsize)
+    grp = _group(W, 1 << 20, cuda_device)
+    np_dt = {torch.float32: np.float32, torch.int64: np.int64, torch.uint8: np.uint8}[dtype]
+    for it in range(4):
+        splits = rng.integers(0, 300, size=(W, W))
+        splits[rng.integers(0, W), rng.integers(0, W)] = 0
+        if it == 3:                                       # equal-split form (no split lists)
+            splits[:] = 64
+        ins_h = [((np.arange(splits[r].sum()) + 1000 * r + 7 * it) % 251).astype(np_dt) for r in range(W)]
+        want = oracle.all_to_all_single(ins_h, splits)
+        ins = [torch.from_numpy(x).to(cuda_device) for x in ins_h]
+        outs = [torch.empty(int(splits[:, r].sum()), dtype=dtype, device=cuda_device) for r in range(W)]
+        if it == 3:
+            _run_all(grp, lambda r, w, st: w.all_to_all_single(outs[r], ins[r], stream=st))
+        else:
+            _run_all(grp, lambda r, w, st: w.all_to_all_single(
+                outs[r], ins[r], [int(splits[s][r]) for s in range(W)], [int(x) for x in splits[r]], stream=st))
+        for r in range(W):
+            assert np.array_equal(outs[r].cpu().numpy(), want[r]), (W, dtype, it, r)
+
+
+def test_zero_copy_output_in_window(cuda_device, oracle):
+    W = 4
+    grp = _group(W, 1 << 20, cuda_device)
+    n = 4096
+    outs = [w.alloc(n, torch.float32)[0] for w in grp.windows]
+    ins_h = [(np.arange(n) + 10000 * r).astype(np.float32) for r in range(W)]
+    ins = [torch.from_numpy(x).to(cuda_device) for x in ins_h]
+    _run_all(grp, lambda r, w, st: w.all_to_all_single(outs[r], ins[r], stream=st))
+    want = oracle.all_to_all_single(ins_h, np.full((W, W), n // W))
+    for r in range(W):
+        assert grp.windows[r].offset_of(outs[r]) is not None
+        assert np.array_equal(outs[r].cpu().numpy(), want[r])
+
+
+@pytest.mark.parametrize("W,T", [(2, 4), (4, 6), (8, 8), (3, 5)])
+def test_pooled_exchange_vs_oracle(cuda_device, oracle, W, T):
+    from param_b200.comms.pt.dlrm import split_lengths
+    E, N = 32, 50
+    ts = split_lengths(T, W)
+    bs = split_lengths(N, W)
+    rng = np.random.default_rng(W + T)
+    pooled_h = [rng.standard_normal((ts[r], N, E)).astype(np.float32) for r in range(W)]
+    want = oracle.pooled_a2a_fwd(pooled_h, bs, ts, E)
+    grp = _group(W, 1 << 20, cuda_device)
+    btd = [torch.from_numpy(p).to(cuda_device).permute(1, 0, 2).contiguous().view(N, -1) for p in pooled_h]
+    outs = _run_all(grp, lambda r, w, st: w.pooled_forward(btd[r], bs, ts, E, layout="BTD", stream=st))
+    for r in range(W):
+        assert np.array_equal(outs[r].cpu().numpy(), want[r])
+    grads_h = [rng.standard_normal((bs[r], T * E)).astype(np.float32) for r in range(W)]
+    want_b = oracle.pooled_a2a_bwd(grads_h, bs, ts, E)
+    grads = [torch.from_numpy(g).to(cuda_device) for g in grads_h]
+    gins = _run_all(grp, lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, out_window_off=1 << 19, stream=st))
+    for r in range(W):
+        got = gins[r].view(N, ts[r], E).permute(1, 0, 2).cpu().numpy()
+        assert np.array_equal(got, want_b[r])
+
+
+def test_missing_peer_times_out_instead_of_hanging(cuda_device):
+    from param_b200.comms.pt.peer_window import PeerWindow
+    grp = PeerWindow.local_group(2, 1 << 12, cuda_device, max_ctas=1, spin_timeout_s=0.2)
+    x = torch.arange(64, dtype=torch.float32, device=cuda_device)
+    grp.windows[0].all_to_all_single(None, x)          # rank 1 never calls
+    torch.cuda.synchronize()
+    assert grp.windows[0].error() == 1
