@@ -56,6 +56,30 @@ def parse_embedding_sizes(spec: str) -> List[int]:
     return [int(v) for v in spec.split("-") if v]
 
 
+def lengths_exchange_splits(tables_split: Sequence[int], rank: int, local_batch: int):
+    """all_to_all splits (in ELEMENTS) of the lengths exchange: rank r receives the lengths of ITS
+    tables from everyone — in-splits T_j*b per destination j, out-splits T_rank*b per source
+    (dlrm.py:768-785)."""
+    in_splits = [int(t) * int(local_batch) for t in tables_split]
+    out_splits = [int(tables_split[rank]) * int(local_batch)] * len(tables_split)
+    return in_splits, out_splits
+
+
+def indices_exchange_counts(lengths: torch.Tensor, lengths_out: torch.Tensor,
+                            tables_split: Sequence[int], local_batch: int):
+    """Index counts per destination (sum of my lengths over the tables each rank owns) and per
+    source (sum of the received lengths of each source block) — the splits of the indices
+    all-to-all (dlrm.py:801-818).  Device tensors int64 [W] each; no host sync here."""
+    W = len(tables_split)
+    per_table = lengths.view(-1, int(local_batch)).sum(dim=1)
+    bounds = torch.tensor([0] + list(torch.tensor(list(tables_split)).cumsum(0).tolist()),
+                          device=lengths.device)
+    csum = torch.cat([per_table.new_zeros(1), per_table.cumsum(0)])
+    send_counts = csum[bounds[1:]] - csum[bounds[:-1]]
+    recv_counts = lengths_out.view(W, -1).sum(dim=1)
+    return send_counts, recv_counts
+
+
 @dataclass
 class SparseBatch:
     """One rank's sparse inputs for its LOCAL batch and ALL global tables (table-major), the
@@ -153,18 +177,13 @@ class DLRMParallelEmbedding:
         W, b, win = self.world, self.b, self.window
         if batch.count != self.T_global or batch.batch_size != b:
             raise PB200Error("SparseBatch does not match the configured tables / local batch")
-        # lengths: in-splits T_r*b per destination, out-splits T_l*b per source (dlrm.py:768-785)
-        in_splits = [t * b for t in self.tables_split]
-        out_splits = [self.T_local * b] * W
+        in_splits, out_splits = lengths_exchange_splits(self.tables_split, self.rank, b)
         lengths_out = win.all_to_all_single(None, batch.lengths, out_splits, in_splits,
                                             out_window_off=self.off_lengths)
         # element counts per destination / per source: the one host round trip (the reference has
         # .item() + two .numpy() here, dlrm.py:801-818)
-        per_table = batch.lengths.view(self.T_global, b).sum(dim=1)
-        bounds = torch.tensor([0] + list(torch.tensor(self.tables_split).cumsum(0).tolist()), device=self.device)
-        csum = torch.cat([per_table.new_zeros(1), per_table.cumsum(0)])
-        send_counts = (csum[bounds[1:]] - csum[bounds[:-1]])
-        recv_counts = lengths_out.view(W, -1).sum(dim=1)
+        send_counts, recv_counts = indices_exchange_counts(batch.lengths, lengths_out,
+                                                           self.tables_split, b)
         counts = torch.stack([send_counts, recv_counts]).cpu()
         idx_in, idx_out = counts[0].tolist(), counts[1].tolist()
         n_recv = int(sum(idx_out))

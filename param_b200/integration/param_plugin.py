@@ -1,0 +1,122 @@
+"""Drop the B200 kernels under the UNMODIFIED reference runners.
+
+Needs the reference importable as `param_bench` (the reference's own import convention,
+train/comms/pt/comms.py:15-36; e.g. `ln -s <param checkout> /tmp/pb/param_bench` and
+PYTHONPATH=/tmp/pb:<param checkout>/train/comms/pt).  On a box without the reference use the
+stand-alone runners in param_b200/comms/pt/ instead.
+
+    # config 3 — the reference's comms.py, b200 backend selected through its own plugin registry
+    torchrun --nproc-per-node 8 -- -m param_b200.integration.param_plugin comms \
+        --backend b200 --device cuda --collective all_to_all_single --b 1K --e 1G --z 1 --c 1
+    #   (comms.py falls through to customized_backend[args.backend], comms.py:1506-1521)
+
+    # config 4 — the reference's dlrm.py (backend class is hard-coded there, dlrm.py:1327-1333, so it
+    # is patched in; the use_device_time shim fixes the reference's start-up crash)
+    torchrun --nproc-per-node 8 -- -m param_b200.integration.param_plugin dlrm --mini-batch-size 8192 ...
+
+    # config 1 — the reference's compute driver with the module swapped (nn.EmbeddingBag -> B200)
+    python -m param_b200.integration.param_plugin emb --device gpu emb --dataset A
+"""
+from __future__ import annotations
+
+import sys
+
+
+def make_backend_class():
+    """class B200ParamBackend(B200CommsMixin, PyTorchDistBackend) against the real reference."""
+    from param_bench.train.comms.pt.pytorch_dist_backend import PyTorchDistBackend
+
+    from ..comms.pt.backend import B200CommsMixin
+
+    class B200ParamBackend(B200CommsMixin, PyTorchDistBackend):
+        def __init__(self, bootstrap_info, commsParams):
+            PyTorchDistBackend.__init__(self, bootstrap_info, commsParams)
+            # the collectiveFunc / computeFunc tables were bound in the base __init__; rebind the
+            # hot-path entries to the overrides (pytorch_backend_utils.py:161-180)
+            self.collectiveFunc["all_to_all_single"] = self.all_to_all_single
+            self.collectiveFunc["all_to_allv"] = self.all_to_allv
+            self.collectiveFunc["all_to_all"] = self.all_to_all
+            self.computeFunc["emb_lookup"] = self.emb_lookup
+
+        # the runner passes its --backend value ("b200") down as the c10d backend name
+        # (comms.py:1527-1532, :1455-1456): bootstrap and pass-through collectives run on NCCL
+        def initialize_backend(self, master_ip, master_port, backend="nccl", eager_mode=False):
+            return PyTorchDistBackend.initialize_backend(
+                self, master_ip, master_port, backend="nccl" if backend == "b200" else backend,
+                eager_mode=eager_mode)
+
+        def initialize_groups(self, groupRanks=None, backend="nccl", force_new_group=False):
+            return PyTorchDistBackend.initialize_groups(
+                self, groupRanks, backend="nccl" if backend == "b200" else backend,
+                force_new_group=force_new_group)
+
+    return B200ParamBackend
+
+
+def register(name: str = "b200"):
+    """register_customized_backend(name, cls) — must run BEFORE the runner parses its arguments
+    (choices are computed at parse time, comms_utils.py:1769-1771)."""
+    from param_bench.train.comms.pt.pytorch_backend_utils import register_customized_backend
+
+    cls = make_backend_class()
+    register_customized_backend(name, cls)
+    return cls
+
+
+def run_comms(argv):
+    register()
+    from param_bench.train.comms.pt import comms
+
+    sys.argv = ["comms.py"] + list(argv)
+    comms.main()
+
+
+def run_dlrm(argv):
+    cls = register()
+    import dlrm  # script-dir import, as the reference does (dlrm.py:17-23)
+
+    orig = dlrm.commsDLRMBench.readArgs
+
+    def read_args(self, parser, defaultModel="dlrm"):
+        args = orig(self, parser, defaultModel)
+        if not hasattr(args, "use_device_time"):
+            args.use_device_time = False
+        return args
+
+    dlrm.commsDLRMBench.readArgs = read_args
+    dlrm.PyTorchDistBackend = cls
+    sys.argv = ["dlrm.py"] + list(argv)
+    dlrm.main()
+
+
+def run_emb(argv):
+    """reference driver.py / pytorch_emb.py with nn.EmbeddingBag replaced by the B200 module for
+    --device gpu (the swap XlaEmbeddingBag makes for tpu, pytorch_emb.py:178-184)."""
+    import pytorch_emb as ref_emb  # reference module (train/compute/pt on sys.path)
+
+    from ..compute.pt.pytorch_emb import B200EmbeddingBag
+
+    class _NN:
+        def __getattr__(self, item):
+            import torch.nn as nn
+            return getattr(nn, item)
+
+        @staticmethod
+        def EmbeddingBag(features, embdim, mode="sum", **kw):
+            return B200EmbeddingBag(features, embdim, mode=mode, **kw)
+
+    ref_emb.nn = _NN()
+    import driver  # reference driver
+
+    sys.argv = ["driver.py"] + list(argv)
+    driver.main()
+
+
+def main():
+    if len(sys.argv) < 2 or sys.argv[1] not in ("comms", "dlrm", "emb"):
+        raise SystemExit("usage: param_plugin {comms|dlrm|emb} <runner args>")
+    {"comms": run_comms, "dlrm": run_dlrm, "emb": run_emb}[sys.argv[1]](sys.argv[2:])
+
+
+if __name__ == "__main__":
+    main()

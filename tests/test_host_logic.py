@@ -1,0 +1,201 @@
+"""Host-side logic on the CPU: generators, size maths, split planning, the plugin surface, and a
+2-rank gloo run of the sparse-input redistribution plan checked against the oracle."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(ROOT / "tests" / "golden"))   # make_golden._ref_paths (reference import helper)
+
+
+def test_init_indices_compat_is_bit_identical_to_reference_golden(golden_dir):
+    from param_b200.compute.pt.pytorch_emb import init_indices
+    d = np.load(golden_dir / "init_indices_ref.npz")
+    f, b, n = (int(x) for x in d["uniform_args"])
+    torch.manual_seed(int(d["uniform_seed"]))
+    assert torch.equal(init_indices(0.0, f, b, n), torch.from_numpy(d["uniform"]))
+    f, b, n = (int(x) for x in d["zipf_args"])
+    np.random.seed(int(d["zipf_seed"]))
+    assert torch.equal(init_indices(float(d["zipf_alpha"]), f, b, n), torch.from_numpy(d["zipf"]))
+    # the driver hands --alpha over as a str (driver.py:44-46): accepted here
+    np.random.seed(int(d["zipf_seed"]))
+    assert torch.equal(init_indices(str(float(d["zipf_alpha"])), f, b, n), torch.from_numpy(d["zipf"]))
+
+
+def test_init_indices_compat_fails_like_the_reference_when_bag_cannot_be_filled():
+    from param_b200.compute.pt.pytorch_emb import init_indices
+    np.random.seed(0)
+    with pytest.raises(ValueError):
+        init_indices(3.0, 50, 64, 20)      # extreme skew: < 20 distinct values among 40 draws
+
+
+def test_zipf_cdf_matches_reference_pmf():
+    from param_b200.compute.pt.pytorch_emb import zipf_cdf
+    cdf = zipf_cdf(1.15, 1000)
+    pmf = np.power(np.arange(1, 1001, dtype=np.float64), -1.15)
+    pmf /= pmf.sum()
+    np.testing.assert_allclose(np.diff(np.concatenate([[0.0], cdf])), pmf, rtol=1e-12, atol=1e-15)
+    assert cdf[-1] == 1.0
+
+
+def test_offsets_and_datasets():
+    from param_b200.compute.pt import dataset
+    from param_b200.compute.pt.pytorch_emb import make_offsets
+    assert make_offsets(4, 20).tolist() == [0, 20, 40, 60]
+    assert len(dataset.emb_A) == 16 and len(dataset.emb_B) == 6
+    assert dataset.emb_A[0] == (14000000, 128, 30, 512) and dataset.emb_A[-1] == (26000000, 128, 30, 65536)
+    assert dataset.emb_B[0] == (4800000, 56, 34, 2048) and dataset.emb_B[-1] == (4800000, 56, 34, 65536)
+    if REF.exists():
+        sys.path.insert(0, str(REF / "train" / "compute" / "pt"))
+        sys.dont_write_bytecode = True
+        import importlib
+        ref_ds = importlib.import_module("dataset")
+        assert list(ref_ds.emb_A) == dataset.emb_A and list(ref_ds.emb_B) == dataset.emb_B
+
+
+def test_module_surface_matches_nn_embeddingbag_contract():
+    from param_b200._cabi import PB200Error
+    from param_b200.compute.pt.pytorch_emb import B200EmbeddingBag
+    emb = B200EmbeddingBag(100, 16, mode="sum")
+    assert tuple(emb.weight.shape) == (100, 16) and emb.weight.element_size() == 4
+    assert abs(float(emb.weight.std()) - 1.0) < 0.2                      # N(0,1) default init
+    with pytest.raises(PB200Error):                                        # no CPU path
+        emb(torch.zeros(4, dtype=torch.int64), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(PB200Error):
+        B200EmbeddingBag(10, 4, mode="max")
+
+
+def test_size_maths():
+    from param_b200.comms.pt.comms import get_sizes, parsesize
+    assert parsesize("1K") == 1024 and parsesize("1G") == 1 << 30 and parsesize("512") == 512
+    assert parsesize("4MB") == 4 << 20
+    assert get_sizes(1024, 8192, 2) == [1024, 2048, 4096, 8192]
+    assert get_sizes(1024, 5000, 4) == [1024, 4096]
+
+
+def test_split_helpers_match_reference():
+    from param_b200.comms.pt.dlrm import lengths_exchange_splits, owner_slice, parse_embedding_sizes, split_lengths
+    assert split_lengths(5, 3) == [2, 2, 1] and split_lengths(8, 8) == [1] * 8 and split_lengths(512, 8) == [64] * 8
+    assert owner_slice(1, [2, 2, 1]) == slice(2, 4)
+    assert parse_embedding_sizes("1000-2000-30") == [1000, 2000, 30]
+    assert parse_embedding_sizes("1000000x4") == [1000000] * 4
+    assert lengths_exchange_splits([2, 2, 1], 2, 4) == ([8, 8, 4], [4, 4, 4])
+    if REF.exists():
+        from make_golden import _ref_paths
+        _ref_paths()
+        import dlrm as ref_dlrm
+        for n, w in [(5, 3), (64, 8), (7, 4), (3, 3)]:
+            for r in range(w):
+                my, splits = ref_dlrm.paramDLRM_Net.get_split_lengths_by_len(None, n, r, w)
+                assert splits == split_lengths(n, w) and my == split_lengths(n, w)[r]
+                ref_sl = ref_dlrm.paramDLRM_Net.get_slice_sparse(None, r, splits, w)
+                assert (ref_sl.start, ref_sl.stop) == (owner_slice(r, splits).start, owner_slice(r, splits).stop)
+
+
+def test_sparse_batch_from_offsets_matches_reference_calculate_lengths(golden_dir):
+    from param_b200.comms.pt.dlrm import SparseBatch
+    d = np.load(golden_dir / "dlrm_sparse_ref.npz")
+    feat = int(d["cl_feat"])
+    offs = [torch.from_numpy(d[f"cl_off{f}"]) for f in range(feat)]
+    idxs = [torch.from_numpy(d[f"cl_idx{f}"]) for f in range(feat)]
+    sb = SparseBatch.from_offsets(offs, idxs, device="cpu")
+    assert sb.count == feat and sb.batch_size == int(d["cl_batch"])
+    assert np.array_equal(sb.lengths.numpy(), d["cl_lengths"])
+    assert np.array_equal(sb.indices.numpy(), d["cl_indices"])
+
+
+def test_backend_surface_is_complete():
+    """every name the reference runners call on a backend exists on B200Backend"""
+    from param_b200.comms.pt.backend import B200Backend
+    needed = """all_to_all_single all_to_all all_to_allv all_reduce reduce broadcast all_gather all_gather_base
+        reduce_scatter_base barrier sync_barrier complete_accel_ops device_sync wait noop gemm emb_lookup
+        get_reduce_op get_mem_size getBusBW alloc_ones alloc_random alloc_empty alloc_embedding_tables
+        clear_memory get_local_rank get_global_rank get_world_size get_local_size get_group_rank
+        get_group_size get_device get_hw_device get_default_group get_groups get_num_pgs get_next_group
+        set_device get_new_stream get_new_event get_current_stream switch_stream sync_stream
+        initialize_backend initialize_groups initialize_tcpstore sayHello benchmark_comms set_up tear_down
+        store_get store_set tensor_list_to_numpy barrier_all_ranks""".split()
+    for name in needed:
+        assert callable(getattr(B200Backend, name, None)), name
+    be = B200Backend.__new__(B200Backend)
+    ca = type("CA", (), {"world_size": 8})()
+    assert abs(B200Backend.getBusBW(be, "all_to_all_single", 100.0, ca) - 87.5) < 1e-9
+    assert abs(B200Backend.getBusBW(be, "all_reduce", 100.0, ca) - 175.0) < 1e-9
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_plugin_registers_with_the_reference_registry():
+    from make_golden import _ref_paths
+    _ref_paths()
+    import inspect
+    from param_b200.integration import param_plugin
+    cls = param_plugin.register("b200")
+    from param_bench.train.comms.pt import pytorch_backend_utils as pbu
+    from param_bench.train.comms.pt.pytorch_dist_backend import PyTorchDistBackend
+    assert pbu.customized_backend["b200"] is cls
+    assert issubclass(cls, PyTorchDistBackend) and not inspect.isabstract(cls)
+    # hot-path entries resolve to the B200 overrides, the rest to the reference's c10d code
+    from param_b200.comms.pt.backend import B200CommsMixin
+    for name in ("all_to_all_single", "all_to_allv", "all_to_all", "emb_lookup", "alloc_empty",
+                 "alloc_embedding_tables", "complete_accel_ops"):
+        assert getattr(cls, name) is getattr(B200CommsMixin, name), name
+    assert cls.all_reduce is PyTorchDistBackend.all_reduce
+
+
+# ---- world_size-2 gloo: the redistribution plan end to end on the CPU -------------------------
+def _dist_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    from param_b200.comms.pt.dlrm import (SparseBatch, indices_exchange_counts, lengths_exchange_splits,
+                                          split_lengths)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, b = 5, 6
+    ts = split_lengths(T, world)
+    rng = np.random.default_rng(100 + rank)
+    offs, idxs = [], []
+    for t in range(T):
+        lens = rng.integers(0, 4, size=b)
+        offs.append(torch.from_numpy(np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)))
+        idxs.append(torch.from_numpy(rng.integers(0, 10**6, size=int(lens.sum())).astype(np.int64)))
+    sb = SparseBatch.from_offsets(offs, idxs, device="cpu")
+    in_s, out_s = lengths_exchange_splits(ts, rank, b)
+    lengths_out = torch.empty(sum(out_s), dtype=torch.int64)
+    dist.all_to_all_single(lengths_out, sb.lengths, out_s, in_s)
+    send, recv = indices_exchange_counts(sb.lengths, lengths_out, ts, b)
+    indices_out = torch.empty(int(recv.sum()), dtype=torch.int64)
+    dist.all_to_all_single(indices_out, sb.indices, recv.tolist(), send.tolist())
+    np.savez(os.path.join(tmp, f"r{rank}.npz"), lengths=sb.lengths.numpy(), indices=sb.indices.numpy(),
+             lengths_out=lengths_out.numpy(), indices_out=indices_out.numpy(),
+             **{f"off{t}": offs[t].numpy() for t in range(T)}, **{f"idx{t}": idxs[t].numpy() for t in range(T)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sparse_redistribution_plan_two_ranks_gloo(oracle, tmp_path):
+    import torch.multiprocessing as mp
+    from param_b200.comms.pt.dlrm import owner_slice, split_lengths
+    W, T, b = 2, 5, 6
+    mp.spawn(_dist_worker, args=(W, 29671, str(tmp_path)), nprocs=W, join=True)
+    data = [np.load(tmp_path / f"r{r}.npz") for r in range(W)]
+    ts = split_lengths(T, W)
+    for r in range(W):
+        Tl = ts[r]
+        sl = owner_slice(r, ts)
+        _, offsets, indices = oracle.split_per_table(data[r]["lengths_out"], data[r]["indices_out"], W, Tl, b)
+        for f in range(Tl):
+            g = sl.start + f
+            lo, hi = offsets[f * W * b], offsets[(f + 1) * W * b]
+            # table g over the global batch == concatenation over ranks of that rank's bags
+            want_idx = np.concatenate([data[s][f"idx{g}"] for s in range(W)])
+            assert np.array_equal(indices[lo:hi], want_idx)
+            starts, base = [], 0
+            for s in range(W):
+                starts.append(data[s][f"off{g}"] + base)
+                base += data[s][f"idx{g}"].size
+            assert np.array_equal(offsets[f * W * b:(f + 1) * W * b] - lo, np.concatenate(starts))
