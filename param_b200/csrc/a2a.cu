@@ -149,7 +149,7 @@ __device__ __forceinline__ void copy_units(unsigned char *dst, long long dst_str
     }
 }
 
-__global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, const int unit_log2) {
+__global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) {
     __shared__ unsigned long long s_epoch;
     __shared__ unsigned long long s_payload;
     const int W = a.world;
@@ -168,13 +168,11 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, 
     }
 
     // 2. push
-    const long long unit = 1ll << unit_log2;
     for (int k = 0; k < W; ++k) {
         // rotation: self first (no handshake needed, overlaps the ready round trip), then
         // destinations staggered by rank and by CTA so every NVSwitch port is busy
         const int j = (k == 0) ? me : (me + 1 + ((k - 1) + blockIdx.x) % (W - 1)) % W;
         const PeerCopy pc = a.copy[j];
-        const long long total_units = (pc.run_bytes >> unit_log2) * pc.rows;
         long long dst_off;
         if (j == me) {
             dst_off = a.recv_off[me];
@@ -187,23 +185,30 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a, 
             __syncthreads();
             dst_off = (long long)s_payload;
         }
-        if (total_units > 0 && dst_off >= 0) {
+        if (pc.rows > 0 && pc.run_bytes > 0 && dst_off >= 0) {
+            unsigned char *dst = a.peer_data[j] + dst_off;
+            // copy unit from the alignment of everything that moves for THIS destination (the
+            // destination offset is chosen by the receiver, so it is only known here)
+            unsigned long long bits = (unsigned long long)pc.src | (unsigned long long)pc.run_bytes |
+                                      (unsigned long long)dst;
+            if (pc.rows > 1)
+                bits |= (unsigned long long)pc.src_stride | (unsigned long long)pc.dst_stride;
+            const int ul = (bits & 15ull) == 0 ? 4 : ((bits & 3ull) == 0 ? 2 : 0);
+            const long long run_units = pc.run_bytes >> ul;
+            const long long total_units = run_units * pc.rows;
             // contiguous slice of units per CTA (keeps each CTA's stores in long runs)
             const long long per = (total_units + gridDim.x - 1) / gridDim.x;
             const long long u0 = per * blockIdx.x;
             const long long u1 = min(u0 + per, total_units);
             if (u0 < u1) {
-                unsigned char *dst = a.peer_data[j] + dst_off;
-                const long long run_units = pc.run_bytes >> unit_log2;
-                if (unit_log2 == 4)
+                if (ul == 4)
                     copy_units<16>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
-                else if (unit_log2 == 2)
+                else if (ul == 2)
                     copy_units<4>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
                 else
                     copy_units<1>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
             }
         }
-        (void)unit;
         // 3. done: last CTA for this destination signals it
         __syncthreads();
         if (threadIdx.x == 0 && j != me) {
@@ -328,22 +333,12 @@ static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, c
     a.spin_cycles = c->spin_cycles;
     a.rank = c->rank;
     a.world = c->world;
-    // common alignment of everything that moves -> copy unit
-    uintptr_t bits = 0;
-    for (int r = 0; r < c->world; ++r) {
-        const PeerCopy &pc = a.copy[r];
-        if (pc.rows == 0 || pc.run_bytes == 0) continue;
-        bits |= (uintptr_t)pc.src | (uintptr_t)pc.run_bytes;
-        if (pc.rows > 1) bits |= (uintptr_t)pc.src_stride | (uintptr_t)pc.dst_stride;
-    }
-    for (int r = 0; r < c->world; ++r) bits |= (uintptr_t)a.recv_off[r] | (uintptr_t)c->peer_data[r];
-    const int unit_log2 = (bits & 15) == 0 ? 4 : ((bits & 3) == 0 ? 2 : 0);
     // grid: one CTA per 256 KB of the largest per-peer block, at least 1, at most the SM count
     long long grid = (max_peer_bytes + (256ll << 10) - 1) / (256ll << 10);
     const int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    a2a_push_kernel<<<(unsigned)grid, kA2AThreads, 0, st>>>(a, unit_log2);
+    a2a_push_kernel<<<(unsigned)grid, kA2AThreads, 0, st>>>(a);
     count_launch();
     PB200_LAUNCH_CHECK();
     return PB200_OK;

@@ -37,6 +37,7 @@ struct BwdParams {
     int num_tables;
     int dim;
     int mean;
+    long long total_rows_hint;
 };
 
 __device__ __forceinline__ void split_bag_bwd(const BwdParams &p, long long gb, int &t,
@@ -155,13 +156,15 @@ __global__ void __launch_bounds__(256) tbe_bwd_generic_kernel(const BwdParams p)
 // SORTED
 // ------------------------------------------------------------------------------------
 // step 1: (key, val) pairs for bags [gb_lo, gb_hi) whose lookups are [i_lo, i_hi).
-//   key = arena row relative to the chunk's first row;  val = global bag id (plain sum) or the
-//   lookup position relative to i_lo (weighted / mean: the weight and bag come from side arrays).
+//   key = arena row relative to the chunk's first row;
+//   val = offset of the bag's gradient row inside grad_out, in float4 units (plain sum), or the
+//         lookup position relative to i_lo (weighted / mean: weight and gradient offset come from
+//         side arrays).  The segmented reduce then needs no division to find a gradient row.
 template <typename index_t, bool SIDE>
 __global__ void __launch_bounds__(256) build_pairs_kernel(const BwdParams p, long long gb_lo,
                                                           long long gb_hi, long long i_lo,
                                                           long long chunk_row0, unsigned *keys,
-                                                          unsigned *vals, unsigned *bag_of,
+                                                          unsigned *vals, unsigned *goff_of,
                                                           float *w_of) {
     // one lane group of 8 per bag keeps the index reads coalesced for typical bag sizes
     constexpr int G = 8;
@@ -176,29 +179,41 @@ __global__ void __launch_bounds__(256) build_pairs_kernel(const BwdParams p, lon
     long long b;
     split_bag_bwd(p, gb, t, b);
     const long long base_row = p.table_row_offsets[t] - chunk_row0;
+    const unsigned goff4 = (unsigned)(((long long)t * p.go_stride_t + b * p.go_stride_b) >> 2);
     const float inv = (p.mean && end > begin) ? 1.f / (float)(end - begin) : 1.f;
     for (long long i = begin + lane_g; i < end; i += G) {
         const long long o = i - i_lo;
         keys[o] = (unsigned)(base_row + ld_index<index_t>(idx + i));
         if (SIDE) {
             vals[o] = (unsigned)o;
-            bag_of[o] = (unsigned)(gb - gb_lo);
+            goff_of[o] = goff4;
             w_of[o] = (p.psw ? p.psw[i] : 1.f) * inv;
         } else {
-            vals[o] = (unsigned)(gb - gb_lo);
+            vals[o] = goff4;
         }
     }
 }
 
-// step 3: segmented reduce over the sorted pairs.  One lane group per SEG sorted entries.
+// step 3: segmented reduce over the sorted pairs.  One lane group per kSeg sorted entries.
+// Batches of U gradient rows are loaded unconditionally (16 B per lane, rows of past-the-end
+// entries alias gradient row 0 and are masked); a batch whose first and last key equal the running
+// key — the common case under skew, where one hot row spans thousands of entries — is added without
+// any per-entry bookkeeping.  Each (segment, row) ends in ONE red.global.add.v4.f32.
 constexpr int kSeg = 64;
+
+__device__ __forceinline__ void add2b(float &a0, float &a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; "
+        "mov.b64 {%0,%1}, ra; }"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
 
 template <int G, int C, bool SIDE>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, long long n,
-                                                             long long gb_lo, long long chunk_row0,
+                                                             long long chunk_row0,
                                                              const unsigned *__restrict__ keys,
                                                              const unsigned *__restrict__ vals,
-                                                             const unsigned *__restrict__ bag_of,
+                                                             const unsigned *__restrict__ goff_of,
                                                              const float *__restrict__ w_of) {
     constexpr int BPW = 32 / G;
     constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
@@ -212,24 +227,30 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, 
     const int my_n = (s0 < n) ? (int)(s1 - s0) : 0;
     const int max_n = (BPW == 1) ? my_n : __reduce_max_sync(0xffffffffu, my_n);
 
-    float4 *d4 = (float4 *)p.dst;
+    float4 *d4 = (float4 *)p.dst + (unsigned long long)chunk_row0 * (unsigned)vec4;
     const unsigned row_stride4 = (unsigned)vec4;
+    const float4 *colp[C];
+    bool col_ok[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int col = c * G + lane_g;
+        col_ok[c] = col < vec4;
+        colp[c] = (const float4 *)p.grad_out + (col_ok[c] ? col : 0);
+    }
     float4 acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned cur_key = 0xffffffffu;
-    bool have = false;
+    unsigned cur_key = 0xffffffffu;   // no arena row has this id (row count < 2^32 - 1)
 
     auto flush = [&]() {
-        if (have) {
-            float4 *rp = d4 + ((unsigned long long)chunk_row0 + cur_key) * row_stride4;
+        if (cur_key != 0xffffffffu) {
+            float4 *rp = d4 + (unsigned long long)cur_key * row_stride4;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const int col = c * G + lane_g;
-                if (col < vec4) {
+                if (col_ok[c]) {
                     float4 v = acc[c];
                     v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-                    red_add_f4(rp + col, v);
+                    red_add_f4(rp + c * G + lane_g, v);
                 }
                 acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -237,64 +258,61 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, 
     };
 
     for (int base = 0; base < max_n; base += G) {
-        unsigned my_key = 0, my_val = 0;
-        float my_w = 1.f;
+        unsigned my_key = 0, my_goff = 0;
+        float my_w = 0.f;
         if (base + lane_g < my_n) {
             my_key = keys[s0 + base + lane_g];
-            my_val = vals[s0 + base + lane_g];
+            my_goff = vals[s0 + base + lane_g];
             if (SIDE) {
-                my_w = w_of[my_val];
-                my_val = bag_of[my_val];
+                my_w = w_of[my_goff];
+                my_goff = goff_of[my_goff];
             }
         }
-        const int cnt = min(G, max_n - base);
+        const int cnt = min(G, max_n - base);    // warp-uniform
+        const int valid = my_n - base;           // this group's remaining entries
         for (int j0 = 0; j0 < cnt; j0 += U) {
             float4 v[U][C];
             unsigned kk[U];
             float ww[U];
-            bool okk[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int j = j0 + u;
-                kk[u] = __shfl_sync(0xffffffffu, my_key, j & (G - 1), G);
-                const unsigned bag = __shfl_sync(0xffffffffu, my_val, j & (G - 1), G);
-                ww[u] = SIDE ? __shfl_sync(0xffffffffu, my_w, j & (G - 1), G) : 1.f;
-                okk[u] = (j < G) && (base + j < my_n);
-                const long long gb = gb_lo + bag;
-                int t;
-                long long b;
-                split_bag_bwd(p, gb, t, b);
-                const float4 *go4 =
-                    (const float4 *)(p.grad_out + (long long)t * p.go_stride_t + b * p.go_stride_b);
+                const int src = (j0 + u) & (G - 1);
+                kk[u] = __shfl_sync(0xffffffffu, my_key, src, G);
+                const unsigned goff = __shfl_sync(0xffffffffu, my_goff, src, G);
+                if (SIDE) ww[u] = __shfl_sync(0xffffffffu, my_w, src, G);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int col = c * G + lane_g;
-                    if (okk[u] && col < vec4)
-                        v[u][c] = ld_row_f4(go4 + col);  // grad rows are re-read ~L times: keep in L1/L2
-                    else
-                        v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(colp[c] + goff);
             }
+            const bool all_valid = (j0 + U <= valid) && (j0 + U <= G);
+            if (!SIDE && all_valid && kk[0] == kk[U - 1] && (kk[0] == cur_key || cur_key == 0xffffffffu)) {
+                cur_key = kk[0];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (okk[u]) {
-                    if (!have || kk[u] != cur_key) {
-                        flush();
-                        cur_key = kk[u];
-                        have = true;
-                    }
+                for (int u = 0; u < U; ++u) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        if (SIDE) {
-                            acc[c].x = fmaf(ww[u], v[u][c].x, acc[c].x);
-                            acc[c].y = fmaf(ww[u], v[u][c].y, acc[c].y);
-                            acc[c].z = fmaf(ww[u], v[u][c].z, acc[c].z);
-                            acc[c].w = fmaf(ww[u], v[u][c].w, acc[c].w);
-                        } else {
-                            acc[c].x += v[u][c].x;
-                            acc[c].y += v[u][c].y;
-                            acc[c].z += v[u][c].z;
-                            acc[c].w += v[u][c].w;
+                        add2b(acc[c].x, acc[c].y, v[u][c].x, v[u][c].y);
+                        add2b(acc[c].z, acc[c].w, v[u][c].z, v[u][c].w);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (j0 + u < valid && j0 + u < G) {
+                        if (kk[u] != cur_key) {
+                            flush();
+                            cur_key = kk[u];
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if (SIDE) {
+                                acc[c].x = fmaf(ww[u], v[u][c].x, acc[c].x);
+                                acc[c].y = fmaf(ww[u], v[u][c].y, acc[c].y);
+                                acc[c].z = fmaf(ww[u], v[u][c].z, acc[c].z);
+                                acc[c].w = fmaf(ww[u], v[u][c].w, acc[c].w);
+                            } else {
+                                add2b(acc[c].x, acc[c].y, v[u][c].x, v[u][c].y);
+                                add2b(acc[c].z, acc[c].w, v[u][c].z, v[u][c].w);
+                            }
                         }
                     }
                 }
@@ -334,11 +352,6 @@ static SortedPlan plan_sorted(long long n_indices, int num_tables, bool side) {
     pl.total_bytes = pl.cub_bytes + 4 * arr + (side ? 2 * arr : 0);
     return pl;
 }
-
-template <typename index_t, int G, int C>
-static int run_sorted(const BwdParams &p, const long long *h_offsets_bounds /*unused*/,
-                      long long total_rows, void *scratch, long long scratch_bytes,
-                      cudaStream_t st);
 
 }  // namespace pb200
 
@@ -405,6 +418,11 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
     PB200_CUDA_TRY(cudaStreamSynchronize(st));
 
     const int vec4 = p.dim >> 2;
+    // gradient row offsets travel as 32-bit float4 indices
+    {
+        const long long last = (long long)(T - 1) * p.go_stride_t + (p.batch - 1) * p.go_stride_b + p.dim;
+        if ((last >> 2) >= 0xffffffffll || p.total_rows_hint >= 0xffffffffll) return PB200_EUNSUPPORTED;
+    }
     int t0 = 0;
     while (t0 < T) {
         int t1 = t0 + 1;
@@ -443,10 +461,10 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         const long long g2 = (n_seg + per_block - 1) / per_block;                               \
         if (side)                                                                               \
             segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, st>>>(                  \
-                p, n, gb_lo, row0, ks, vs, bag_of, w_of);                                       \
+                p, n, row0, ks, vs, bag_of, w_of);                                              \
         else                                                                                    \
             segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(                 \
-                p, n, gb_lo, row0, ks, vs, nullptr, nullptr);                                   \
+                p, n, row0, ks, vs, nullptr, nullptr);                                          \
     } while (0)
             if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
             else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);

@@ -63,8 +63,26 @@ __device__ __forceinline__ void split_bag(const FwdParams &p, long long gb, int 
     }
 }
 
+// Packed fp32 adds (Blackwell FADD2 / FFMA2): two IEEE round-to-nearest fp32 lanes per instruction,
+// bit-identical to two scalar adds, half the issue slots.
+__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; "
+        "mov.b64 {%0,%1}, ra; }"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float &a0, float &a1, float w, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb, rw; mov.b64 ra, {%0,%1}; mov.b64 rb, {%3,%4}; mov.b64 rw, {%2,%2}; "
+        "fma.rn.f32x2 ra, rw, rb, ra; mov.b64 {%0,%1}, ra; }"
+        : "+f"(a0), "+f"(a1)
+        : "f"(w), "f"(b0), "f"(b1));
+}
+
 // Accumulate one bag (or, for G < 32, 32/G bags side by side) given per-group [begin, end).
-// IdxSrc abstracts where index i of the bag comes from (global memory or the staged bucket).
+// The hot loop is branch- and predicate-free: rows are consumed in batches of 8/4/2/1 whose size is
+// warp-uniform, every lane issues its loads unconditionally (lanes beyond dim/4 read column 0 and
+// drop the result at the store), and only groups shorter than the longest bag of the warp mask
+// their tail.  Per row and warp that is 1 SHFL + 1 IMAD.WIDE + 1 LDG.128 + 2 FADD2.
 template <typename index_t, int G, int C, bool WEIGHTED, int U>
 struct BagAccum {
     float4 acc[C];
@@ -74,17 +92,71 @@ struct BagAccum {
         for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
+    // N rows starting at lane j of the group; MASKED: rows at or beyond `valid` are dropped
+    template <int N, bool MASKED>
+    __device__ __forceinline__ void batch(const float4 *const (&colp)[C], unsigned row_stride4,
+                                          unsigned my_row, float my_w, int j, int valid) {
+        float4 v[N][C];
+        float wv[N];
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const unsigned row = __shfl_sync(0xffffffffu, my_row, j + u, G);
+            if (WEIGHTED) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u, G);
+            const unsigned long long roff = (unsigned long long)row * row_stride4;
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(colp[c] + roff);
+        }
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const bool drop = MASKED && (j + u >= valid);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float4 x = v[u][c];
+                if (MASKED && drop) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (WEIGHTED) {
+                    const float w = (MASKED && drop) ? 0.f : wv[u];
+                    fma2(acc[c].x, acc[c].y, w, x.x, x.y);
+                    fma2(acc[c].z, acc[c].w, w, x.z, x.w);
+                } else {
+                    add2(acc[c].x, acc[c].y, x.x, x.y);
+                    add2(acc[c].z, acc[c].w, x.z, x.w);
+                }
+            }
+        }
+    }
+
+    template <bool MASKED>
+    __device__ __forceinline__ void span(const float4 *const (&colp)[C], unsigned row_stride4,
+                                         unsigned my_row, float my_w, int j, int end, int valid) {
+        for (; j + U <= end; j += U) batch<U, MASKED>(colp, row_stride4, my_row, my_w, j, valid);
+        if (U > 4 && j + 4 <= end) {
+            batch<4, MASKED>(colp, row_stride4, my_row, my_w, j, valid);
+            j += 4;
+        }
+        if (U > 2 && j + 2 <= end) {
+            batch<2, MASKED>(colp, row_stride4, my_row, my_w, j, valid);
+            j += 2;
+        }
+        for (; j < end; ++j) batch<1, MASKED>(colp, row_stride4, my_row, my_w, j, valid);
+    }
+
     // idx_ptr: pointer to this group's first index (global or shared); len: this group's bag
-    // length; maxlen: warp-uniform max over the groups of the warp.
+    // length; minlen / maxlen: warp-uniform min / max over the groups of the warp.
     template <bool FROM_SMEM>
     __device__ __forceinline__ void run(const FwdParams &p, const index_t *idx_ptr,
                                         const float *psw_ptr, long long base_row, int len,
-                                        int maxlen, int lane_g, int vec4) {
-        const float4 *w4 = (const float4 *)p.weights;
-        const unsigned row_stride4 = (unsigned)(p.dim >> 2);
+                                        int minlen, int maxlen, int lane_g, int vec4) {
+        const unsigned row_stride4 = (unsigned)vec4;
+        const float4 *colp[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int col = c * G + lane_g;
+            colp[c] = (const float4 *)p.weights + (col < vec4 ? col : 0);
+        }
         for (int base = 0; base < maxlen; base += G) {
-            // one coalesced read of up to G indices per group
-            unsigned my_row = 0;
+            // one coalesced read of up to G indices per group; out-of-bag lanes keep row 0 of the
+            // group's table, which is a valid address and masked out below
+            unsigned my_row = (unsigned)base_row;
             float my_w = 0.f;
             if (base + lane_g < len) {
                 long long ix;
@@ -95,44 +167,14 @@ struct BagAccum {
                 my_row = (unsigned)(base_row + ix);
                 if (WEIGHTED) my_w = ld_stream_f32(psw_ptr + base + lane_g);
             }
-            const int cnt = min(G, maxlen - base);  // warp-uniform
-            for (int j0 = 0; j0 < cnt; j0 += U) {
-                float4 v[U][C];
-                float wv[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = j0 + u;
-                    const unsigned row = __shfl_sync(0xffffffffu, my_row, j & (G - 1), G);
-                    if (WEIGHTED) wv[u] = __shfl_sync(0xffffffffu, my_w, j & (G - 1), G);
-                    const bool ok = (j < G) && (base + j < len);
-                    const float4 *rp = w4 + (unsigned long long)row * row_stride4;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const int col = c * G + lane_g;
-                        if (ok && col < vec4)
-                            v[u][c] = ld_row_f4(rp + col);
-                        else
-                            v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        if (WEIGHTED) {
-                            acc[c].x = fmaf(wv[u], v[u][c].x, acc[c].x);
-                            acc[c].y = fmaf(wv[u], v[u][c].y, acc[c].y);
-                            acc[c].z = fmaf(wv[u], v[u][c].z, acc[c].z);
-                            acc[c].w = fmaf(wv[u], v[u][c].w, acc[c].w);
-                        } else {
-                            acc[c].x += v[u][c].x;
-                            acc[c].y += v[u][c].y;
-                            acc[c].z += v[u][c].z;
-                            acc[c].w += v[u][c].w;
-                        }
-                    }
-                }
+            const int full = min(G, minlen - base);   // rows every group of the warp still has
+            const int most = min(G, maxlen - base);   // rows the longest group still has
+            int j = 0;
+            if (full > 0) {
+                span<false>(colp, row_stride4, my_row, my_w, 0, full, 0);
+                j = full;
             }
+            if (j < most) span<true>(colp, row_stride4, my_row, my_w, j, most, len - base);
         }
     }
 
@@ -184,13 +226,14 @@ __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) 
     }
     const int len = (int)(end - begin);
     const int maxlen = (BPW == 1) ? len : __reduce_max_sync(0xffffffffu, len);
+    const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
     const long long base_row = (active && p.table_row_offsets) ? p.table_row_offsets[t] : 0;
 
     BagAccum<index_t, G, C, WEIGHTED, U> acc;
     acc.zero();
     acc.template run<false>(p, (const index_t *)p.indices + begin,
-                            WEIGHTED ? p.psw + begin : nullptr, base_row, len, maxlen, lane_g,
-                            vec4);
+                            WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen, maxlen,
+                            lane_g, vec4);
     if (active) acc.store(p, t, b, len, lane_g, vec4);
 }
 
@@ -327,17 +370,18 @@ __global__ void __launch_bounds__((kStagedWarps + 1) * 32) tbe_fwd_staged_kernel
             }
             const int len = (int)(end - begin);
             const int maxlen = (BPW == 1) ? len : __reduce_max_sync(0xffffffffu, len);
+            const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
             const long long base_row =
                 (active && p.table_row_offsets) ? p.table_row_offsets[t] : 0;
             BagAccum<index_t, G, C, WEIGHTED, U> acc;
             acc.zero();
             if (staged)
                 acc.template run<true>(p, s_idx + (begin - begin_al),
-                                       WEIGHTED ? p.psw + begin : nullptr, base_row, len, maxlen,
-                                       lane_g, vec4);
+                                       WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen,
+                                       maxlen, lane_g, vec4);
             else
                 acc.template run<false>(p, g_idx + begin, WEIGHTED ? p.psw + begin : nullptr,
-                                        base_row, len, maxlen, lane_g, vec4);
+                                        base_row, len, minlen, maxlen, lane_g, vec4);
             if (active) acc.store(p, t, b, len, lane_g, vec4);
         }
         __syncwarp();
@@ -462,7 +506,8 @@ static int dispatch_fwd(FwdParams &p, int algo, long long total_rows_hint, cudaS
         PB200_LAUNCH_CHECK();
         return PB200_OK;
     }
-    if (algo == PB200_FWD_AUTO) algo = PB200_FWD_STAGED;
+    // measured on B200 (profiles/): DIRECT beats STAGED by 15-35 %, so AUTO = DIRECT
+    if (algo == PB200_FWD_AUTO) algo = PB200_FWD_DIRECT;
     // bulk copies need 16 B-aligned index/offset arrays
     if ((((uintptr_t)p.indices | (uintptr_t)p.offsets) & 15) != 0) algo = PB200_FWD_DIRECT;
     if (algo == PB200_FWD_STAGED) {
