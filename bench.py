@@ -213,6 +213,7 @@ def run_b200(args):
     ms_fwd = ev_time(fwd, args.steps)
     ms_bwd = ev_time(bwd, args.steps)
     ms_fwd_direct = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="direct", out=out), args.steps)
+    ms_fwd_staged = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="staged", out=out), args.steps)
     ms_bwd_other = None
     other = "atomic" if bwd_algo == "sorted" else "sorted"
     try:
@@ -257,7 +258,7 @@ def run_b200(args):
                          algorithmic_bytes=dom_bytes, ms=round(dom_ms, 4)),
         "kernels": {"fwd": dict(roof(fwd_bytes, ms_fwd), ms=round(ms_fwd, 4), lookups_per_s=lookups / ms_fwd * 1e3,
                                 param_bw_gbs=round(lookups * D * 4 / ms_fwd / 1e6, 1)),
-                    "fwd_direct_ms": round(ms_fwd_direct, 4),
+                    "fwd_direct_ms": round(ms_fwd_direct, 4), "fwd_staged_ms": round(ms_fwd_staged, 4),
                     "bwd": dict(roof(bwd_bytes, ms_bwd), ms=round(ms_bwd, 4), algo=bwd_algo),
                     f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4)},
         "clocks": clk.summary(),
@@ -286,7 +287,7 @@ def run_e2e(args, arena, idx, off, lookups):
     h_off = torch.empty(off.numel(), dtype=torch.int64).pin_memory()
     h_idx.copy_(idx)
     h_off.copy_(off)
-    h_out = torch.empty((B, T * D), dtype=torch.float32).pin_memory()
+    h_out = torch.empty((T, B, D), dtype=torch.float32).pin_memory()   # [T, B, D]: contiguous D2H per group
     tro_h = arena.row_offsets.cpu()
     ctx = C.c_void_p()
     _cabi.check(lib.pb200_host_ctx_create(C.byref(ctx), g * B * L + 16, g * B, D), "host_ctx_create")
@@ -294,7 +295,7 @@ def run_e2e(args, arena, idx, off, lookups):
     def call():
         _cabi.check(lib.pb200_tbe_step_host(ctx, arena.weights.data_ptr(), arena.row_offsets.data_ptr(),
                                             tro_h.data_ptr(), T, D, h_idx.data_ptr(), h_idx.numel(),
-                                            h_off.data_ptr(), B, 0, h_out.data_ptr(), 0, g,
+                                            h_off.data_ptr(), B, 0, h_out.data_ptr(), 1, g,
                                             1, C.c_float(-args.lr)), "tbe_step_host")
 
     for _ in range(2):
@@ -324,7 +325,9 @@ def cpu_baseline(args, arena, idx, rows, backward):
     ids = [idx[t * B * L:(t + 1) * B * L].cpu() for t in range(n)]
     offs = [torch.arange(B, dtype=torch.int64) * L for _ in range(n)]
     sec, threads = ref_torch_cpu.time_embeddingbag_cpu(ws, ids, offs, steps=3, warmups=1, backward=backward)
+    sec_f, _ = ref_torch_cpu.time_embeddingbag_cpu(ws, ids, offs, steps=5, warmups=2, backward=False)
     return {"value": n * B * L / sec, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(),
+            "fwd_only_value": n * B * L / sec_f, "fwd_only_ms_per_step_sample": sec_f * 1e3,
             "kind": "reference",
             "sample": f"torch.nn.EmbeddingBag(mode=sum, sparse=True) fwd+bwd on the host, first {n} of {T} tables "
                       f"({rows} rows x {D}), same Zipf indices, 3 steps after 1 warm-up (measure_cpu loop, "

@@ -399,7 +399,9 @@ extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t 
     const long long E = emb_dim;
     // the pushed run is one (row, table) cell of E floats unless the local layout already has the
     // tables adjacent inside a row (in_stride_t == E), in which case it is the whole T_local*E run
-    const bool tables_adjacent = (in_stride_t == E) || T_local <= 1;
+    // NB: the choice must be the same on every rank (it fixes the number of collectives), so it
+    // depends on the layout alone, never on this rank's table count.
+    const bool tables_adjacent = (in_stride_t == E);
     if (!tables_adjacent) {
         // [T, N, E]-style input (dlrm.py torch.stack layout): one 2-D push per local table.
         // Every rank must run the same number of rounds (epochs advance in lock step), so the
