@@ -179,7 +179,7 @@ def test_backward_zipf_hot_rows(cuda_device, oracle):
 def test_check_indices(cuda_device):
     from param_b200 import ops
     tro = torch.tensor([0, 10, 30], dtype=torch.int64, device=cuda_device)
-    idx = torch.tensor([0, 9, 10, 5, 29, 30, -1], dtype=torch.int64, device=cuda_device)
+    idx = torch.tensor([0, 9, 10, 5, 19, 30, -1], dtype=torch.int64, device=cuda_device)
     off = torch.tensor([0, 2, 3, 5, 7], dtype=torch.int64, device=cuda_device)  # T=2, B=2
     assert ops.check_indices(tro, 2, idx, off, 2) == 3  # 10 (table 0), 30 and -1 (table 1)
 
@@ -278,3 +278,50 @@ def test_host_buffer_entry(cuda_device, oracle):
                                            h_off.data_ptr(), B, 0, h_out.data_ptr(), layout, 4))
         assert np.array_equal(h_out.numpy(), oracle.tbe_fwd(arena, tro, dim, idx, offsets, B, layout=name))
     lib.pb200_host_ctx_destroy(ctx)
+
+
+def test_tbe_module_fused_sgd(cuda_device, oracle):
+    """B200TBE: forward(indices, offsets, per_sample_weights) + out.backward(grad) with the optimizer
+    fused into the backward (how pytorch_dist_backend.py:832-857 drives the TBE op)."""
+    from param_b200.compute.tbe import B200TBE
+    rng = np.random.default_rng(3)
+    T, B, dim = 3, 128, 64
+    specs = [(200, dim), (300, dim), (150, dim)]
+    op = B200TBE(specs, lr=0.1, device=cuda_device)
+    lens = rng.integers(0, 9, size=T * B)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = np.concatenate([rng.integers(0, specs[t][0], size=int(lens[t * B:(t + 1) * B].sum())) for t in range(T)]).astype(np.int64)
+    w0 = op.weights.detach().cpu().numpy().copy()
+    tro = op.arena.row_offsets.cpu().numpy()
+    out = op.forward(_t(idx, cuda_device), _t(offsets, cuda_device), None)
+    assert np.array_equal(out.detach().cpu().numpy(), oracle.tbe_fwd(w0, tro, dim, idx, offsets, B))
+    g = torch.randn_like(out)
+    out.backward(g)
+    want = w0.astype(np.float64) + oracle.tbe_bwd(int(tro[-1]), tro, dim, idx, offsets, B, g.cpu().numpy(),
+                                                  scale=-0.1, dtype=np.float64)
+    assert np.abs(op.weights.detach().cpu().numpy() - want).max() <= RTOL * np.abs(want).max()
+
+
+def test_et_replay_style_dispatch(cuda_device, oracle):
+    """et_replay rebuilds an op from node.name + node.op_schema through TorchScript IR
+    (et_replay/et_replay_utils.py:171-212); the b200:: ops must be callable that way."""
+    import param_b200.et  # noqa: F401  (what the replay config's "import modules" does)
+    ir = """
+graph(%0: Tensor, %1: Tensor, %2: Tensor, %3: int, %4: Tensor?, %5: bool):
+    %output: Tensor = b200::embedding_bag(%0, %1, %2, %3, %4, %5)
+    return (%output)
+"""
+    fn = torch._C.CompilationUnit().create_function("b200::embedding_bag", torch._C.parse_ir(ir))
+    rng = np.random.default_rng(8)
+    w = rng.standard_normal((100, 128)).astype(np.float32)
+    idx = rng.integers(0, 100, size=60).astype(np.int64)
+    off = (np.arange(12) * 5).astype(np.int64)
+    out = fn(_t(w, cuda_device), _t(idx, cuda_device), _t(off, cuda_device), 0, None, False)
+    assert np.array_equal(out.cpu().numpy(), oracle.embbag_fwd(w, idx, off))
+    tro = torch.tensor([0, 100], dtype=torch.int64, device=cuda_device)
+    off1 = _t(np.concatenate([off, [60]]), cuda_device)
+    out2 = torch.ops.b200.tbe_forward(_t(w, cuda_device), tro, 128, _t(idx, cuda_device), off1, 12, 0, None, 0)
+    assert torch.equal(out2, out)
+    dst = torch.zeros(100, 128, device=cuda_device)
+    torch.ops.b200.tbe_backward_(dst, tro, 128, _t(idx, cuda_device), off1, 12, torch.ones(12, 128, device=cuda_device), 0, 1.0, 0, 1)
+    assert torch.equal(dst[:, 0].cpu(), torch.bincount(torch.from_numpy(idx), minlength=100).float())
