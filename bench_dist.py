@@ -87,6 +87,10 @@ def run_dist(args):
     ms_a2a_f = maxr(ev_time(lambda: win.pooled_forward(pooled, model.batch_split, model.tables_split, D,
                                                        out_window_off=model.off_pooled), args.steps))
     dist.barrier()
+    ms_fused = maxr(ev_time(lambda: win.lookup_forward_fused(model.arena, indices, offsets, model.batch_split,
+                                                             model.tables_split, out_window_off=model.off_pooled),
+                            args.steps))
+    dist.barrier()
     out = state["out"]
     ms_a2a_b = maxr(ev_time(lambda: win.pooled_backward(out, model.batch_split, model.tables_split, D,
                                                         out_window_off=model.off_grad), args.steps))
@@ -169,7 +173,8 @@ def run_dist(args):
         "roofline": {"bound": "hbm", "kernel": "lookup_" + dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 4), "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes": dom_bytes, "ms": round(dom_ms, 4)},
-        "pieces_ms": {"sparse_input_dist": ms_dist, "lookup_fwd": ms_lookup, "a2a_fwd_fused_permute": ms_a2a_f,
+        "pieces_ms": {"sparse_input_dist": ms_dist, "fused_lookup_a2a_fwd_one_kernel": ms_fused,
+                      "lookup_fwd": ms_lookup, "a2a_fwd_fused_permute": ms_a2a_f,
                       "a2a_bwd_fused_permute": ms_a2a_b, "scatter_add_bwd": ms_scatter},
         "a2a": {"bytes_per_rank": S, "fwd_busbw_gbs": bus(ms_a2a_f), "bwd_busbw_gbs": bus(ms_a2a_b),
                 "frac_of_measured_peer_copy_770": bus(ms_a2a_f) / NVLINK_PEAK_MEASURED,

@@ -224,6 +224,19 @@ int pb200_a2a_pooled_bwd(pb200_a2a_comm *comm, const float *grad /* [lN, T_globa
                          const int64_t *tables_split, int64_t out_window_off,
                          void *stream);
 
+/* Fused lookup + exchange, ONE kernel per rank: the batched EmbeddingBag forward over this
+ * rank's tables for the GLOBAL batch (TBE request: offsets[T_local*N + 1]) whose epilogue stores
+ * every pooled row directly into the owning rank's final [lN, T_global*E] tensor in its window —
+ * apply_emb + All2Allv_Req/Wait + both torch.cat of dlrm.py:363-388, :86-177, :1253 in one launch,
+ * with the NVLink transfer of one bag overlapping the gather of the next.  Same epoch protocol as
+ * pb200_a2a_single (the calls can be mixed on one communicator). */
+int pb200_tbe_fwd_a2a(pb200_a2a_comm *comm, const float *weights,
+                      const int64_t *table_row_offsets, int32_t num_tables_local, int32_t dim,
+                      const void *indices, int64_t n_indices, const void *offsets,
+                      int32_t idx_type, int32_t pool_mode,
+                      const int64_t *batch_split, const int64_t *tables_split,
+                      int64_t out_window_off, void *stream);
+
 /* =========================================================================
  * 6. Sparse-input regroup (integer, bit-exact)
  * =========================================================================

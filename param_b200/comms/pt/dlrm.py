@@ -169,6 +169,7 @@ class DLRMParallelEmbedding:
         _, self.off_grad = self.window.alloc(self.N * T_max * self.E, torch.float32)
         self._pooled_local = torch.empty((self.N, self.T_local * self.E), dtype=torch.float32, device=device)
         self._saved = None
+        self.fused = True
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------
     def sparse_data_dist(self, batch: SparseBatch):
@@ -196,10 +197,15 @@ class DLRMParallelEmbedding:
         return offsets, indices
 
     # ---- steps 3+4: apply_emb + forward all-to-all ------------------------------------------------
-    def forward(self, offsets: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
-        """lookup for the global batch, then the fused exchange; returns [lN, T_global*E]."""
-        ops.tbe_forward(self.arena, indices, offsets, self.N, layout="BTD", out=self._pooled_local)
+    def forward(self, offsets: torch.Tensor, indices: torch.Tensor, fused: Optional[bool] = None) -> torch.Tensor:
+        """lookup for the global batch + exchange; returns [lN, T_global*E].  fused=True (default):
+        ONE kernel whose epilogue stores pooled rows into the peers' windows (pb200_tbe_fwd_a2a);
+        fused=False: lookup kernel to a local [N, T_l*E] buffer, then the push kernel."""
         self._saved = (offsets, indices)
+        if self.fused if fused is None else fused:
+            return self.window.lookup_forward_fused(self.arena, indices, offsets, self.batch_split,
+                                                    self.tables_split, out_window_off=self.off_pooled)
+        ops.tbe_forward(self.arena, indices, offsets, self.N, layout="BTD", out=self._pooled_local)
         return self.window.pooled_forward(self._pooled_local, self.batch_split, self.tables_split, self.E,
                                           layout="BTD", out_window_off=self.off_pooled)
 

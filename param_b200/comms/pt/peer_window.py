@@ -256,6 +256,27 @@ class PeerWindow:
         lN, Tg = int(batch_split[self.rank]), int(sum(tables_split))
         return self.view(out_window_off, lN * Tg * E, torch.float32).view(lN, Tg * E)
 
+    def lookup_forward_fused(self, arena, indices: torch.Tensor, offsets: torch.Tensor,
+                             batch_split: Sequence[int], tables_split: Sequence[int],
+                             mode: str = "sum", out_window_off: int = 0, stream=None) -> torch.Tensor:
+        """ONE kernel: batched lookup of this rank's tables for the global batch, pooled rows stored
+        straight into every destination's [lN, T_global*E] tensor (pb200_tbe_fwd_a2a).  `arena` is an
+        ops.TableArena with tables_split[rank] tables; offsets has T_local*N + 1 entries."""
+        if not indices.is_cuda or indices.dtype != offsets.dtype:
+            raise PB200Error("lookup_forward_fused needs CUDA indices/offsets of one integer dtype")
+        it = {torch.int64: 0, torch.int32: 1}[indices.dtype]
+        E, N = arena.dim, int(sum(batch_split))
+        if offsets.numel() != arena.num_tables * N + 1:
+            raise PB200Error("offsets must have T_local*N + 1 entries")
+        rc = _cabi.load().pb200_tbe_fwd_a2a(
+            self._comm, arena.weights.data_ptr(), arena.row_offsets.data_ptr(), arena.num_tables, E,
+            indices.data_ptr(), indices.numel(), offsets.data_ptr(), it, {"sum": 0, "mean": 1}[mode],
+            _cabi.i64_array(batch_split), _cabi.i64_array(tables_split), int(out_window_off),
+            self._stream(stream))
+        _cabi.check(rc, "pb200_tbe_fwd_a2a")
+        lN, Tg = int(batch_split[self.rank]), int(sum(tables_split))
+        return self.view(out_window_off, lN * Tg * E, torch.float32).view(lN, Tg * E)
+
     def pooled_backward(self, grad: torch.Tensor, batch_split: Sequence[int],
                         tables_split: Sequence[int], emb_dim: int, out_window_off: int = 0,
                         stream=None) -> torch.Tensor:

@@ -29,113 +29,117 @@
 // No CTA ever waits on another CTA of the same grid, so the grid need not be co-resident.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "a2a_common.cuh"
 
 namespace pb200 {
 
-struct SignalPad {
-    unsigned long long ready_epoch[PB200_A2A_MAX_RANKS];
-    unsigned long long ready_payload[PB200_A2A_MAX_RANKS];
-    unsigned long long done_epoch[PB200_A2A_MAX_RANKS];
-};
-static_assert(sizeof(SignalPad) <= PB200_A2A_SIGNAL_BYTES, "signal pad too small");
-
-struct PeerCopy {
-    const unsigned char *src;   // local
-    long long src_stride;       // bytes between rows
-    long long dst_stride;       // bytes between rows in the destination window
-    long long run_bytes;        // contiguous bytes per row
-    long long rows;
-};
-
-struct A2AArgs {
-    unsigned char *peer_data[PB200_A2A_MAX_RANKS];
-    SignalPad *peer_pad[PB200_A2A_MAX_RANKS];
-    PeerCopy copy[PB200_A2A_MAX_RANKS];            // what I send to each destination
-    long long recv_off[PB200_A2A_MAX_RANKS];       // where source r must write inside MY window
-    unsigned long long *epoch;                      // device: last completed epoch
-    unsigned *peer_cnt;                             // device [W]: CTAs finished per destination
-    unsigned *grid_cnt;                             // device: CTAs finished overall
-    unsigned *error;                                // device: set to 1 when a spin wait timed out
-    long long spin_cycles;                          // give up a flag wait after this many clocks
-    int rank;
-    int world;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ int4 ld_src_v4(const int4 *p) {
-    int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_peer_v4(int4 *p, const int4 &v) {
-    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-
-// Bounded spin on a flag in local memory: a peer that never arrives (crashed rank, mismatched
-// call sequence) must not hang the GPU — after spin_cycles the kernel records an error and moves on.
-__device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, unsigned long long e,
-                                             long long budget, unsigned *err) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < e) {
-        if (clock64() - t0 > budget) {
-            atomicExch(err, 1u);
-            return false;
-        }
-    }
-    return true;
-}
-
 constexpr int kA2AThreads = 512;
-constexpr int kA2AUnroll = 4;
+constexpr int kA2AUnroll = 8;
 
-// copy units [u0, u1) of one destination; a unit is UNIT bytes; run_units = units per row
+// contiguous copy of n 16 B units: kA2AUnroll independent loads in flight per thread
+__device__ __forceinline__ void copy_linear16(int4 *__restrict__ dst, const int4 *__restrict__ src,
+                                              long long n) {
+    long long u = threadIdx.x;
+    const long long step = kA2AThreads;
+    for (; u + (kA2AUnroll - 1) * step < n; u += kA2AUnroll * step) {
+        int4 v[kA2AUnroll];
+#pragma unroll
+        for (int k = 0; k < kA2AUnroll; ++k) v[k] = ld_src_v4(src + u + k * step);
+#pragma unroll
+        for (int k = 0; k < kA2AUnroll; ++k) st_peer_v4(dst + u + k * step, v[k]);
+    }
+    for (; u < n; u += step) st_peer_v4(dst + u, ld_src_v4(src + u));
+}
+
+// Copy units [u0, u1) of one destination's 2-D block; a unit is UNIT bytes, run_units = units per
+// row.  No division in the steady state: rows are walked explicitly.
 template <int UNIT>
 __device__ __forceinline__ void copy_units(unsigned char *dst, long long dst_stride,
                                            const unsigned char *src, long long src_stride,
-                                           long long run_units, long long u0, long long u1) {
+                                           long long run_units, long long rows, long long u0,
+                                           long long u1) {
     if (UNIT == 16) {
-        long long u = u0 + threadIdx.x;
-        const long long step = (long long)kA2AThreads;
-        // unrolled main loop: kA2AUnroll independent 16 B loads in flight per thread
-        for (; u + (kA2AUnroll - 1) * step < u1; u += kA2AUnroll * step) {
-            int4 v[kA2AUnroll];
-            long long doff[kA2AUnroll];
-#pragma unroll
-            for (int k = 0; k < kA2AUnroll; ++k) {
-                const long long uu = u + k * step;
-                const long long r = uu / run_units;
-                const long long c = uu - r * run_units;
-                v[k] = ld_src_v4((const int4 *)(src + r * src_stride) + c);
-                doff[k] = r * dst_stride + c * 16;
-            }
-#pragma unroll
-            for (int k = 0; k < kA2AUnroll; ++k) st_peer_v4((int4 *)(dst + doff[k]), v[k]);
+        if (rows == 1 || (src_stride == run_units * 16 && dst_stride == run_units * 16)) {
+            // one contiguous range (all_to_all_single, or rows that happen to be adjacent)
+            copy_linear16((int4 *)dst + u0, (const int4 *)src + u0, u1 - u0);
+            return;
         }
-        for (; u < u1; u += step) {
-            const long long r = u / run_units;
-            const long long c = u - r * run_units;
-            const int4 v = ld_src_v4((const int4 *)(src + r * src_stride) + c);
-            st_peer_v4((int4 *)(dst + r * dst_stride + c * 16), v);
+        long long r = u0 / run_units;           // one division per (CTA, destination)
+        long long c = u0 - r * run_units;
+        long long left = u1 - u0;
+        if (run_units >= kA2AThreads && (run_units % kA2AThreads) == 0 && c == 0 &&
+            (left % run_units) == 0) {
+            // long rows (e.g. 64 tables x 128 floats = 2048 units): thread t owns columns
+            // t + k*512; (row, k) advance incrementally so kA2AUnroll loads are always in flight,
+            // also across row boundaries
+            const int per_row = (int)(run_units / kA2AThreads);
+            const long long iters = (left / run_units) * per_row;
+            const unsigned char *sp = src + r * src_stride + (long long)threadIdx.x * 16;
+            unsigned char *dp = dst + r * dst_stride + (long long)threadIdx.x * 16;
+            int k = 0;
+            long long it = 0;
+            for (; it + kA2AUnroll <= iters; it += kA2AUnroll) {
+                int4 v[kA2AUnroll];
+                unsigned char *d[kA2AUnroll];
+#pragma unroll
+                for (int j = 0; j < kA2AUnroll; ++j) {
+                    v[j] = ld_src_v4((const int4 *)(sp + (long long)k * kA2AThreads * 16));
+                    d[j] = dp + (long long)k * kA2AThreads * 16;
+                    if (++k == per_row) {
+                        k = 0;
+                        sp += src_stride;
+                        dp += dst_stride;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kA2AUnroll; ++j) st_peer_v4((int4 *)d[j], v[j]);
+            }
+            for (; it < iters; ++it) {
+                st_peer_v4((int4 *)(dp + (long long)k * kA2AThreads * 16),
+                           ld_src_v4((const int4 *)(sp + (long long)k * kA2AThreads * 16)));
+                if (++k == per_row) {
+                    k = 0;
+                    sp += src_stride;
+                    dp += dst_stride;
+                }
+            }
+        } else if (run_units >= kA2AThreads) {
+            // long rows, general: the whole CTA streams one row segment at a time
+            while (left > 0) {
+                const long long n = min(run_units - c, left);
+                copy_linear16((int4 *)(dst + r * dst_stride) + c, (const int4 *)(src + r * src_stride) + c, n);
+                left -= n;
+                c = 0;
+                ++r;
+            }
+        } else {
+            // short rows: a thread owns a column, rows advance by blockDim / run_units per step
+            // (only valid if run_units divides the block; otherwise fall back to per-unit division)
+            const int ru = (int)run_units;
+            if ((kA2AThreads % ru) == 0 && c == 0 && (left % ru) == 0) {
+                const int col = threadIdx.x % ru;
+                const long long rstep = kA2AThreads / ru;
+                const long long r_end = r + left / ru;     // u1 - u0 is a multiple of run_units here
+                long long rr = r + threadIdx.x / ru;
+                for (; rr + (kA2AUnroll - 1) * rstep < r_end; rr += kA2AUnroll * rstep) {
+                    int4 v[kA2AUnroll];
+#pragma unroll
+                    for (int k = 0; k < kA2AUnroll; ++k)
+                        v[k] = ld_src_v4((const int4 *)(src + (rr + k * rstep) * src_stride) + col);
+#pragma unroll
+                    for (int k = 0; k < kA2AUnroll; ++k)
+                        st_peer_v4((int4 *)(dst + (rr + k * rstep) * dst_stride) + col, v[k]);
+                }
+                for (; rr < r_end; rr += rstep)
+                    st_peer_v4((int4 *)(dst + rr * dst_stride) + col,
+                               ld_src_v4((const int4 *)(src + rr * src_stride) + col));
+            } else {
+                for (long long u = u0 + threadIdx.x; u < u1; u += kA2AThreads) {
+                    const long long rr = u / run_units, cc = u - rr * run_units;
+                    st_peer_v4((int4 *)(dst + rr * dst_stride) + cc,
+                               ld_src_v4((const int4 *)(src + rr * src_stride) + cc));
+                }
+            }
         }
     } else {
         for (long long u = u0 + threadIdx.x; u < u1; u += kA2AThreads) {
@@ -196,17 +200,24 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
             const int ul = (bits & 15ull) == 0 ? 4 : ((bits & 3ull) == 0 ? 2 : 0);
             const long long run_units = pc.run_bytes >> ul;
             const long long total_units = run_units * pc.rows;
-            // contiguous slice of units per CTA (keeps each CTA's stores in long runs)
-            const long long per = (total_units + gridDim.x - 1) / gridDim.x;
-            const long long u0 = per * blockIdx.x;
-            const long long u1 = min(u0 + per, total_units);
+            // contiguous slice per CTA (long store runs); whole rows when the block is 2-D
+            long long u0, u1;
+            if (pc.rows > 1 && pc.rows >= (long long)gridDim.x) {
+                const long long rper = (pc.rows + gridDim.x - 1) / gridDim.x;
+                u0 = min(rper * blockIdx.x, pc.rows) * run_units;
+                u1 = min(rper * (blockIdx.x + 1), pc.rows) * run_units;
+            } else {
+                const long long per = (total_units + gridDim.x - 1) / gridDim.x;
+                u0 = min(per * blockIdx.x, total_units);
+                u1 = min(u0 + per, total_units);
+            }
             if (u0 < u1) {
                 if (ul == 4)
-                    copy_units<16>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+                    copy_units<16>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
                 else if (ul == 2)
-                    copy_units<4>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+                    copy_units<4>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
                 else
-                    copy_units<1>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, u0, u1);
+                    copy_units<1>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
             }
         }
         // 3. done: last CTA for this destination signals it
@@ -243,19 +254,6 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
 
 using namespace pb200;
 
-struct pb200_a2a_comm {
-    int rank;
-    int world;
-    long long window_bytes;
-    unsigned char *peer_data[PB200_A2A_MAX_RANKS];
-    SignalPad *peer_pad[PB200_A2A_MAX_RANKS];
-    unsigned long long *d_epoch;
-    unsigned *d_peer_cnt;
-    unsigned *d_grid_cnt;
-    unsigned *d_error;
-    long long spin_cycles;
-    int max_ctas;
-};
 
 extern "C" int pb200_a2a_comm_create(pb200_a2a_comm **comm, int32_t rank, int32_t world,
                                      void *const *peer_data, void *const *peer_signal,
@@ -333,8 +331,8 @@ static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, c
     a.spin_cycles = c->spin_cycles;
     a.rank = c->rank;
     a.world = c->world;
-    // grid: one CTA per 256 KB of the largest per-peer block, at least 1, at most the SM count
-    long long grid = (max_peer_bytes + (256ll << 10) - 1) / (256ll << 10);
+    // grid: one CTA per 64 KB of the largest per-peer block, at least 1, at most the SM count
+    long long grid = (max_peer_bytes + (64ll << 10) - 1) / (64ll << 10);
     const int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;

@@ -134,3 +134,39 @@ def test_missing_peer_times_out_instead_of_hanging(cuda_device):
     grp.windows[0].all_to_all_single(None, x)          # rank 1 never calls
     torch.cuda.synchronize()
     assert grp.windows[0].error() == 1
+
+
+@pytest.mark.parametrize("W,T,dim", [(2, 4, 128), (4, 6, 64), (8, 9, 128), (3, 5, 56)])
+def test_fused_lookup_exchange_vs_oracle(cuda_device, oracle, W, T, dim):
+    """pb200_tbe_fwd_a2a: lookup + exchange + permute in ONE kernel per rank, bit-exact against
+    oracle lookup -> oracle pooled exchange; then again on the same communicator (epochs), mixed
+    with a plain all_to_all_single."""
+    from param_b200 import ops
+    from param_b200.comms.pt.dlrm import split_lengths
+    rng = np.random.default_rng(W * 31 + T)
+    ts, b = split_lengths(T, W), 24
+    bs = [b] * W
+    N = b * W
+    grp = _group(W, 4 << 20, cuda_device)
+    for rep in range(2):
+        arenas, reqs, pooled_ref = [], [], []
+        for r in range(W):
+            rows = rng.integers(30, 200, size=ts[r])
+            tro = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+            w = rng.standard_normal((int(tro[-1]), dim)).astype(np.float32)
+            lens = rng.integers(0, 12, size=ts[r] * N)
+            off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            idx = np.concatenate([rng.integers(0, rows[t], size=int(lens[t * N:(t + 1) * N].sum()))
+                                  for t in range(ts[r])]).astype(np.int64)
+            arenas.append(ops.TableArena(torch.from_numpy(w).to(cuda_device), torch.from_numpy(tro).to(cuda_device),
+                                         list(rows), dim))
+            reqs.append((torch.from_numpy(idx).to(cuda_device), torch.from_numpy(off).to(cuda_device)))
+            pooled_ref.append(oracle.tbe_fwd(w, tro, dim, idx, off, N, layout="TBD"))
+        want = oracle.pooled_a2a_fwd(pooled_ref, bs, ts, dim)
+        outs = _run_all(grp, lambda r, w_, st: w_.lookup_forward_fused(arenas[r], reqs[r][0], reqs[r][1], bs, ts, stream=st))
+        for r in range(W):
+            assert np.array_equal(outs[r].cpu().numpy(), want[r]), (rep, r)
+        xs = [torch.full((W * 8,), float(r), device=cuda_device) for r in range(W)]
+        ys = _run_all(grp, lambda r, w_, st: w_.all_to_all_single(None, xs[r], out_window_off=2 << 20, stream=st).clone())
+        for r in range(W):
+            assert ys[r].view(W, 8)[:, 0].tolist() == [float(s) for s in range(W)]

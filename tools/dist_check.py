@@ -167,7 +167,9 @@ gath = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(gath, mine)
 pooled_all = [gath[r][:ts[r]].cpu().numpy() for r in range(world)]
 want_out = oracle.pooled_a2a_fwd(pooled_all, [b] * world, ts, E)[rank]
-report("DLRM forward (lookup + fused exchange) == oracle (bit-exact)", np.array_equal(out.cpu().numpy(), want_out))
+report("DLRM forward (ONE fused lookup+exchange kernel) == oracle (bit-exact)", np.array_equal(out.cpu().numpy(), want_out))
+out2 = model.forward(offsets, indices, fused=False).clone()
+report("DLRM forward (lookup kernel + push kernel) == oracle (bit-exact)", np.array_equal(out2.cpu().numpy(), want_out))
 gs = [torch.empty_like(gsum) for _ in range(world)]
 dist.all_gather(gs, gsum)
 gin_ref = oracle.pooled_a2a_bwd([g_.cpu().numpy() for g_ in gs], [b] * world, ts, E)[rank]     # [T_l, N, E]
