@@ -120,7 +120,8 @@ model = DLRMParallelEmbedding(dist.group.WORLD, [rows] * T_g, E, b, L, dev, lr=l
 batch = SparseBatch.synthetic([rows] * T_g, b, L, False, seed=100 + rank, device=dev)
 w0 = model.arena.weights.clone()
 offsets, indices = model.sparse_data_dist(batch)
-out = model.forward(offsets, indices)
+out2 = model.forward(offsets, indices, fused=False).clone()   # lookup kernel + push kernel
+out = model.forward(offsets, indices)                         # ONE fused kernel (default)
 gsum = out * 0.5 + 1.0                                       # some dOut that depends on the data
 model.backward(gsum)
 torch.cuda.synchronize()
@@ -168,7 +169,6 @@ dist.all_gather(gath, mine)
 pooled_all = [gath[r][:ts[r]].cpu().numpy() for r in range(world)]
 want_out = oracle.pooled_a2a_fwd(pooled_all, [b] * world, ts, E)[rank]
 report("DLRM forward (ONE fused lookup+exchange kernel) == oracle (bit-exact)", np.array_equal(out.cpu().numpy(), want_out))
-out2 = model.forward(offsets, indices, fused=False).clone()
 report("DLRM forward (lookup kernel + push kernel) == oracle (bit-exact)", np.array_equal(out2.cpu().numpy(), want_out))
 gs = [torch.empty_like(gsum) for _ in range(world)]
 dist.all_gather(gs, gsum)
