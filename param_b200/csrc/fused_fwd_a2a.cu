@@ -93,17 +93,22 @@ __global__ void __launch_bounds__(256) tbe_fwd_a2a_kernel(const FusedArgs a) {
             // destination of batch row b
             int j = 0;
             while (j + 1 < W && b >= a.n_base[j + 1]) ++j;
-            long long dst_off = s_dst_off[j];
-            if (dst_off == -1) {
-                // first store of this CTA to rank j: wait for its ready flag (one lane spins on
-                // the local pad; the value is then cached in shared memory for the whole CTA)
-                if (lane_g == 0) {
+            // The group leader resolves the destination offset (first store of this CTA to rank j:
+            // wait for j's ready flag on the local pad, then cache the offset in shared memory) and
+            // broadcasts it.  Explicit group mask + __syncwarp: lanes of a group may not be
+            // converged here, and different groups of a warp can target different ranks.
+            const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+            __syncwarp(gmask);
+            long long dst_off = 0;
+            if (lane_g == 0) {
+                dst_off = s_dst_off[j];
+                if (dst_off == -1) {
                     const bool ok = wait_flag_ge(&my_pad->ready_epoch[j], e, a.spin_cycles, a.error);
                     dst_off = ok ? (long long)ld_relaxed_sys(&my_pad->ready_payload[j]) : -2;
                     s_dst_off[j] = dst_off;
                 }
-                dst_off = __shfl_sync(__activemask(), dst_off, lane & ~(G - 1));
             }
+            dst_off = __shfl_sync(gmask, dst_off, lane & ~(G - 1));
             if (dst_off >= 0) {
                 float4 *o = (float4 *)(a.peer_data[j] + dst_off + (b - a.n_base[j]) * a.row_bytes) +
                             (long long)t * vec4;
