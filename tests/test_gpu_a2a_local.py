@@ -18,6 +18,7 @@ def _run_all(grp, fn):
     """launch fn(rank, window, stream) for every virtual rank, then synchronise and check errors"""
     outs = []
     for r, (w, st) in enumerate(zip(grp.windows, grp.streams)):
+        st.wait_stream(torch.cuda.current_stream())   # inputs were produced on the current stream
         with torch.cuda.stream(st):
             outs.append(fn(r, w, st))
     torch.cuda.synchronize()
@@ -104,16 +105,16 @@ def test_zero_copy_output_in_window(cuda_device, oracle):
         assert np.array_equal(outs[r].cpu().numpy(), want[r])
 
 
-@pytest.mark.parametrize("W,T", [(2, 4), (4, 6), (8, 8), (3, 5)])
-def test_pooled_exchange_vs_oracle(cuda_device, oracle, W, T):
+@pytest.mark.parametrize("W,T,E", [(2, 4, 32), (4, 6, 32), (8, 8, 32), (3, 5, 32), (2, 128, 128), (2, 32, 128), (4, 96, 128)])
+def test_pooled_exchange_vs_oracle(cuda_device, oracle, W, T, E):
     from param_b200.comms.pt.dlrm import split_lengths
-    E, N = 32, 50
+    N = 50
     ts = split_lengths(T, W)
     bs = split_lengths(N, W)
     rng = np.random.default_rng(W + T)
     pooled_h = [rng.standard_normal((ts[r], N, E)).astype(np.float32) for r in range(W)]
     want = oracle.pooled_a2a_fwd(pooled_h, bs, ts, E)
-    grp = _group(W, 1 << 20, cuda_device)
+    grp = _group(W, 16 << 20, cuda_device)
     btd = [torch.from_numpy(p).to(cuda_device).permute(1, 0, 2).contiguous().view(N, -1) for p in pooled_h]
     outs = _run_all(grp, lambda r, w, st: w.pooled_forward(btd[r], bs, ts, E, layout="BTD", stream=st))
     for r in range(W):
@@ -121,7 +122,7 @@ def test_pooled_exchange_vs_oracle(cuda_device, oracle, W, T):
     grads_h = [rng.standard_normal((bs[r], T * E)).astype(np.float32) for r in range(W)]
     want_b = oracle.pooled_a2a_bwd(grads_h, bs, ts, E)
     grads = [torch.from_numpy(g).to(cuda_device) for g in grads_h]
-    gins = _run_all(grp, lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, out_window_off=1 << 19, stream=st))
+    gins = _run_all(grp, lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, out_window_off=8 << 20, stream=st))
     for r in range(W):
         got = gins[r].view(N, ts[r], E).permute(1, 0, 2).cpu().numpy()
         assert np.array_equal(got, want_b[r])

@@ -30,6 +30,7 @@ off_pool, off_grad = off_idx + cap_idx * 8, off_idx + cap_idx * 8 + b * T_g * E 
 def run_all(fn):
     outs = []
     for r, (w, st) in enumerate(zip(grp.windows, grp.streams)):
+        st.wait_stream(torch.cuda.current_stream())   # inputs were produced on the current stream
         with torch.cuda.stream(st):
             outs.append(fn(r, w, st))
     torch.cuda.synchronize()
@@ -69,10 +70,26 @@ pooled = [ops.tbe_forward(arenas[r], reqs[r][2], reqs[r][1], N, layout="BTD") fo
 f1 = [t.clone() for t in run_all(lambda r, w, st: w.pooled_forward(pooled[r], bs, ts, E, out_window_off=off_pool, stream=st))]
 f2 = run_all(lambda r, w, st: w.lookup_forward_fused(arenas[r], reqs[r][2], reqs[r][1], bs, ts,
                                                      out_window_off=off_pool, stream=st))
+def diag(name, got, want):
+    if torch.equal(got, want):
+        return True
+    bad = (got != want)
+    nz = bad.nonzero()
+    print(f"MISMATCH {name}: {int(bad.sum())} of {bad.numel()} elements; first at {nz[0].tolist()}, last at {nz[-1].tolist()}; "
+          f"rows affected {int(bad.any(dim=1).sum())} of {bad.shape[0]}; cols affected {int(bad.any(dim=0).sum())} of {bad.shape[1]}; "
+          f"got there {got[tuple(nz[0].tolist())].item()} want {want[tuple(nz[0].tolist())].item()}", flush=True)
+    cols = bad.any(dim=0).nonzero().view(-1)
+    rws = bad.any(dim=1).nonzero().view(-1)
+    print("  bad col range", int(cols.min()), int(cols.max()), " bad row range", int(rws.min()), int(rws.max()), flush=True)
+    return False
+
+
+okall = True
 for r in range(W):
     want = torch.cat([pooled[s][r * b:(r + 1) * b] for s in range(W)], dim=1)
-    assert torch.equal(f1[r], want), f"push fwd rank {r}"
-    assert torch.equal(f2[r], want), f"fused fwd rank {r}"
+    okall &= diag(f"push fwd rank {r}", f1[r], want)
+    okall &= diag(f"fused fwd rank {r}", f2[r], want)
+assert okall
 print("pooled forward (push) and fused lookup+exchange ok")
 grads = [torch.randn(b, T_g * E, device=dev) for _ in range(W)]
 gb = run_all(lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, out_window_off=off_grad, stream=st))
