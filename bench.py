@@ -214,6 +214,7 @@ def run_b200(args):
     ms_bwd = ev_time(bwd, args.steps)
     ms_fwd_direct = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="direct", out=out), args.steps)
     ms_fwd_staged = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="staged", out=out), args.steps)
+    ms_fwd_pipe = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="pipelined", out=out), args.steps)
     ms_bwd_other = None
     other = "atomic" if bwd_algo == "sorted" else "sorted"
     try:
@@ -266,7 +267,7 @@ def run_b200(args):
                              traffic=traffic.get("bwd"), algorithmic_bytes=bwd_bytes, ms=round(ms_bwd, 4)),
         "kernels": {"fwd": dict(roof(fwd_bytes, ms_fwd), ms=round(ms_fwd, 4), lookups_per_s=lookups / ms_fwd * 1e3,
                                 param_bw_gbs=round(lookups * D * 4 / ms_fwd / 1e6, 1)),
-                    "fwd_direct_ms": round(ms_fwd_direct, 4), "fwd_staged_ms": round(ms_fwd_staged, 4),
+                    "fwd_direct_ms": round(ms_fwd_direct, 4), "fwd_staged_ms": round(ms_fwd_staged, 4), "fwd_pipelined_ms": round(ms_fwd_pipe, 4),
                     "bwd": dict(roof(bwd_bytes, ms_bwd), ms=round(ms_bwd, 4), algo=bwd_algo),
                     f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4)},
         "clocks": clk.summary(),
@@ -354,6 +355,14 @@ def run_reference(args):
         return
     T, B, L, D = args.tables, args.batch, args.bag, args.dim
     rows = args.rows
+    tag = "cfg2"
+    if args.gpus > 1:
+        # N > 1: the b200 arm runs cfg4 (64 tables/GPU, local batch 8192): the CPU arm samples the
+        # per-rank lookup of that workload (tables of one rank over the global batch)
+        T = int(os.environ.get("PB200_TABLES_PER_GPU", 64))
+        B = int(os.environ.get("PB200_LOCAL_BATCH", 8192)) * args.gpus
+        rows = int(os.environ.get("PB200_ROWS", min(args.rows, 2_000_000)))
+        tag = "cfg4 (one rank's tables over the global batch)"
     n = min(args.cpu_tables, T)
     rng = np.random.default_rng(2026)
     cdf = zipf_cdf(args.alpha, rows) if args.alpha > 0 else np.linspace(1.0 / rows, 1.0, rows)
@@ -371,7 +380,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2 sample: {sample}", "tables": T, "rows_per_table": rows, "dim": D,
+        "config": {"workload": f"{tag} sample: {sample}", "tables": T, "rows_per_table": rows, "dim": D,
                    "batch": B, "bag": L, "alpha": args.alpha},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(),
                          "kind": "reference", "sample": sample},

@@ -49,6 +49,7 @@ extern "C" {
 #define PB200_FWD_AUTO 0
 #define PB200_FWD_DIRECT 1 /* one lane-group per bag, indices read straight from HBM  */
 #define PB200_FWD_STAGED 2 /* persistent CTAs, cp.async.bulk (TMA) index staging      */
+#define PB200_FWD_PIPELINED 3 /* persistent CTAs, register software pipeline over bags  */
 
 /* backward kernel variants */
 #define PB200_BWD_AUTO 0

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
 
 POOL_SUM, POOL_MEAN = 0, 1
 IDX_I64, IDX_I32 = 0, 1
-FWD_AUTO, FWD_DIRECT, FWD_STAGED = 0, 1, 2
+FWD_AUTO, FWD_DIRECT, FWD_STAGED, FWD_PIPELINED = 0, 1, 2, 3
 BWD_AUTO, BWD_ATOMIC, BWD_SORTED = 0, 1, 2
 A2A_SIGNAL_BYTES = 4096
 A2A_MAX_RANKS = 16

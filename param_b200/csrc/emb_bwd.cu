@@ -15,6 +15,8 @@
 //          are duplicates, so the number of L2 read-modify-writes drops ~8x and hot rows no longer
 //          serialise on one L2 slice; rows wholly inside a segment are updated exactly once
 //          (deterministic), only runs crossing a segment boundary are combined by a few reds.
+#include <stdlib.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -383,6 +385,10 @@ template <typename index_t>
 static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes, cudaStream_t st) {
     const bool side = (p.psw != nullptr) || p.mean;
     const int T = p.num_tables;
+    static const int sort_bits = [] {
+        const char *e = getenv("PB200_SORT_BITS");   // 0 = full key; default 16 (two radix passes)
+        return e ? atoi(e) : 16;
+    }();
     SortedPlan pl = plan_sorted(p.n_indices, T, true);
     const long long need = (long long)pl.total_bytes + 256 + (long long)(T + 1) * 8;
     if (!scratch || scratch_bytes < need) return PB200_EINVAL;
@@ -448,9 +454,13 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
             PB200_LAUNCH_CHECK();
             cub::DoubleBuffer<unsigned> dk(k0, k1), dv(v0, v1);
             size_t tmp = pl.cub_bytes;
-            PB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, dk, dv, (int)n, 0,
-                                                           bits_for((unsigned long long)(row1 - row0)),
-                                                           st));
+            // Grouping, not ordering, is what the segmented reduce needs: sorting on the low
+            // `sort_bits` of the row id (stable) keeps equal rows adjacent except where two rows of
+            // one table share those bits — rare for the rows that matter (hot rows have distinct
+            // low bits) — and costs one radix pass less than a full-key sort.
+            int key_bits = bits_for((unsigned long long)(row1 - row0));
+            if (sort_bits > 0 && key_bits > sort_bits) key_bits = sort_bits;
+            PB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, dk, dv, (int)n, 0, key_bits, st));
             count_launch(4);  // onesweep: histogram + scan + digit passes (library kernels)
             const unsigned *ks = dk.Current();
             const unsigned *vs = dv.Current();

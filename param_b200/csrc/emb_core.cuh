@@ -125,10 +125,11 @@ struct BagAccum {
 
     // idx_ptr: pointer to this group's first index (global or shared); len: this group's bag
     // length; minlen / maxlen: warp-uniform min / max over the groups of the warp.
-    template <bool FROM_SMEM>
+    template <bool FROM_SMEM, bool PRELOADED = false>
     __device__ __forceinline__ void run(const FwdParams &p, const index_t *idx_ptr,
                                         const float *psw_ptr, long long base_row, int len,
-                                        int minlen, int maxlen, int lane_g, int vec4) {
+                                        int minlen, int maxlen, int lane_g, int vec4,
+                                        unsigned pre_row = 0, float pre_w = 0.f) {
         const unsigned row_stride4 = (unsigned)vec4;
         const float4 *colp[C];
 #pragma unroll
@@ -141,7 +142,11 @@ struct BagAccum {
             // group's table, which is a valid address and masked out below
             unsigned my_row = (unsigned)base_row;
             float my_w = 0.f;
-            if (base + lane_g < len) {
+            if (PRELOADED && base == 0) {
+                // first chunk of indices was fetched one bag ahead (software pipeline)
+                my_row = pre_row;
+                my_w = pre_w;
+            } else if (base + lane_g < len) {
                 long long ix;
                 if (FROM_SMEM)
                     ix = (long long)idx_ptr[base + lane_g];

@@ -58,6 +58,82 @@ __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) 
 }
 
 // ------------------------------------------------------------------------------------
+// PIPELINED variant: persistent grid, register software pipeline across bags
+// ------------------------------------------------------------------------------------
+// Each lane group walks bags gb, gb + S, gb + 2S, ... (S = lane groups in the grid) and keeps
+// three bags in flight: the offsets of bag i+2 and the first index chunk of bag i+1 are requested
+// BEFORE the rows of bag i are gathered, so the offsets -> indices -> rows chain of a bag overlaps
+// the row gather of its predecessors instead of being paid in sequence (no shared memory, so the
+// whole 228 KB stays L1 for hot rows).
+template <typename index_t, int G, int C, bool WEIGHTED>
+__global__ void __launch_bounds__(256) tbe_fwd_pipelined_kernel(const FwdParams p) {
+    constexpr int BPW = 32 / G;
+    constexpr int U = UnrollFor<C>::value;
+    const int lane = threadIdx.x & 31;
+    const int lane_g = lane & (G - 1);
+    const int grp = lane / G;
+    const int vec4 = p.dim >> 2;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * BPW;
+    long long gb = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
+    const index_t *idx = (const index_t *)p.indices;
+
+    // stage registers: (b0,e0,row0,w0) current bag, (b1,e1) next, (b2,e2) the one after
+    long long b0 = 0, e0 = 0, b1 = 0, e1 = 0, b2 = 0, e2 = 0;
+    unsigned row0 = 0, row1 = 0;
+    float w0 = 0.f, w1 = 0.f;
+    int t0 = 0, t1 = 0;
+    long long bb0 = 0, bb1 = 0, base_row0 = 0, base_row1 = 0;
+
+    auto fetch_range = [&](long long g, long long &b, long long &e) {
+        b = 0;
+        e = 0;
+        if (g < p.n_bags) bag_range<index_t>(p, g, b, e);
+    };
+    auto fetch_first_chunk = [&](long long g, long long b, long long e, int &t, long long &bb,
+                                 long long &base_row, unsigned &row, float &w) {
+        t = 0;
+        bb = 0;
+        base_row = 0;
+        row = 0;
+        w = 0.f;
+        if (g < p.n_bags) {
+            split_bag(p, g, t, bb);
+            base_row = p.table_row_offsets ? p.table_row_offsets[t] : 0;
+            row = (unsigned)base_row;
+            if (lane_g < (int)(e - b)) {
+                row = (unsigned)(base_row + ld_index<index_t>(idx + b + lane_g));
+                if (WEIGHTED) w = ld_stream_f32(p.psw + b + lane_g);
+            }
+        }
+    };
+
+    fetch_range(gb, b0, e0);
+    fetch_range(gb + stride, b1, e1);
+    fetch_first_chunk(gb, b0, e0, t0, bb0, base_row0, row0, w0);
+
+    // warp-uniform trip count: the first group of the warp has the smallest bag id
+    const long long gb_warp = gb - grp;
+    for (long long it = gb_warp; it < p.n_bags; it += stride, gb += stride) {
+        // requests for the bags behind the current one (consumed one / two iterations later)
+        fetch_range(gb + 2 * stride, b2, e2);
+        fetch_first_chunk(gb + stride, b1, e1, t1, bb1, base_row1, row1, w1);
+
+        const bool active = gb < p.n_bags;
+        const int len = (int)(e0 - b0);
+        const int maxlen = (BPW == 1) ? len : __reduce_max_sync(0xffffffffu, len);
+        const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
+        BagAccum<index_t, G, C, WEIGHTED, U> acc;
+        acc.zero();
+        acc.template run<false, true>(p, idx + b0, WEIGHTED ? p.psw + b0 : nullptr, base_row0, len,
+                                      minlen, maxlen, lane_g, vec4, row0, w0);
+        if (active) acc.store(p, t0, bb0, len, lane_g, vec4);
+
+        b0 = b1; e0 = e1; row0 = row1; w0 = w1; t0 = t1; bb0 = bb1; base_row0 = base_row1;
+        b1 = b2; e1 = e2;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // STAGED variant: persistent, warp-specialised CTAs + cp.async.bulk index/offset staging
 // ------------------------------------------------------------------------------------
 // CTA = kStagedWarps consumer warps + 1 producer warp.  Tile = NB consecutive bags
@@ -296,6 +372,17 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
         if (grid > n_tiles) grid = n_tiles;
         if (grid < 1) grid = 1;
         kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
+    } else if (algo == PB200_FWD_PIPELINED) {
+        auto kern = weighted ? tbe_fwd_pipelined_kernel<index_t, G, C, true>
+                             : tbe_fwd_pipelined_kernel<index_t, G, C, false>;
+        int per_sm = 1;
+        PB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sm_count() * per_sm;  // persistent: a multiple of the SM count
+        const long long need = (p.n_bags + 8ll * BPW - 1) / (8ll * BPW);
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        kern<<<(unsigned)grid, 256, 0, st>>>(p);
     } else {
         const int warps_per_block = 8;
         const long long bags_per_block = (long long)warps_per_block * BPW;
@@ -366,7 +453,7 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_STAGED) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weights;
     p.table_row_offsets = (const long long *)table_row_offsets;
@@ -402,7 +489,7 @@ extern "C" int pb200_embbag_fwd(const float *weight, int64_t num_rows, int32_t d
     if (num_rows < 0 || dim < 1 || n_bags < 0 || n_indices < 0 || out_row_stride < dim)
         return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_STAGED) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weight;
     p.table_row_offsets = nullptr;

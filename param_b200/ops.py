@@ -17,7 +17,7 @@ from ._cabi import (BWD_ATOMIC, BWD_AUTO, BWD_SORTED, FWD_AUTO, FWD_DIRECT, FWD_
                     IDX_I32, IDX_I64, POOL_MEAN, POOL_SUM, PB200Error)
 
 _MODE = {"sum": POOL_SUM, "mean": POOL_MEAN}
-_FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED}
+_FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED, "pipelined": _cabi.FWD_PIPELINED}
 _BWD_ALGO = {"auto": BWD_AUTO, "atomic": BWD_ATOMIC, "sorted": BWD_SORTED}
 
 

@@ -27,7 +27,7 @@ def _t(a, dev, dtype=None):
     return t.to(dev)
 
 
-@pytest.mark.parametrize("algo", ["direct", "staged"])
+@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined"])
 @pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
 def test_forward_golden(cuda_device, golden_dir, algo, idx_dtype):
     from param_b200 import ops
@@ -77,7 +77,7 @@ def _random_tbe(rng, T, B, dim, max_len, rows_lo=50, rows_hi=400, fixed_len=None
 
 
 @pytest.mark.parametrize("dim", [128, 64, 56, 256, 8])
-@pytest.mark.parametrize("algo", ["direct", "staged"])
+@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined"])
 @pytest.mark.parametrize("layout", ["BTD", "TBD"])
 def test_tbe_forward_vs_oracle_ragged(cuda_device, oracle, dim, algo, layout):
     from param_b200 import ops
@@ -90,7 +90,7 @@ def test_tbe_forward_vs_oracle_ragged(cuda_device, oracle, dim, algo, layout):
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("algo", ["direct", "staged"])
+@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined"])
 def test_tbe_forward_odd_alignment_and_tail(cuda_device, oracle, algo):
     """odd total index count, odd bag starts, int32 indices: exercises the 16 B alignment logic of
     the bulk-copy staging and its direct fallback on the last tile."""
@@ -112,7 +112,7 @@ def test_tbe_forward_mean_and_weighted(cuda_device, oracle):
     rows, tro, arena, offsets, idx = _random_tbe(rng, T, B, dim, 30)
     psw = rng.random(idx.size).astype(np.float32) + 0.5
     ar = ops.TableArena(_t(arena, cuda_device), _t(tro, cuda_device), list(rows), dim)
-    for algo in ("direct", "staged"):
+    for algo in ("direct", "staged", "pipelined"):
         out = ops.tbe_forward(ar, _t(idx, cuda_device), _t(offsets, cuda_device), B, mode="mean", algo=algo)
         np.testing.assert_allclose(out.cpu().numpy(), oracle.tbe_fwd(arena, tro, dim, idx, offsets, B, mode="mean"),
                                    rtol=RTOL, atol=1e-6)
@@ -226,7 +226,8 @@ def test_large_shape_properties(cuda_device):
     assert bool((srt[:, 1:] != srt[:, :-1]).all())
     out_d = ops.tbe_forward(ar, idx, off, B, algo="direct")
     out_s = ops.tbe_forward(ar, idx, off, B, algo="staged")
-    assert torch.equal(out_d, out_s)                                     # variants agree bit for bit
+    out_p = ops.tbe_forward(ar, idx, off, B, algo="pipelined")
+    assert torch.equal(out_d, out_s) and torch.equal(out_d, out_p)       # variants agree bit for bit
     # linearity: lookup(2W) == 2 lookup(W) exactly (power-of-two scaling commutes with rounding)
     ar.weights.mul_(2.0)
     assert torch.equal(ops.tbe_forward(ar, idx, off, B), out_d * 2.0)

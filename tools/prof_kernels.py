@@ -40,6 +40,8 @@ for what in a.what.split(","):
     for _ in range(a.iters):
         if what == "fwd_direct":
             ops.tbe_forward(arena, idx, off, B, algo="direct", out=out)
+        elif what == "fwd_pipelined":
+            ops.tbe_forward(arena, idx, off, B, algo="pipelined", out=out)
         elif what == "fwd_staged":
             ops.tbe_forward(arena, idx, off, B, algo="staged", out=out)
         elif what == "bwd_sorted":
