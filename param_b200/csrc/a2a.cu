@@ -36,11 +36,46 @@ namespace pb200 {
 constexpr int kA2AThreads = 512;
 constexpr int kA2AUnroll = 8;
 
+// 256-bit global accesses (Blackwell LDG.E.256 / STG.E.256): 32 B per lane, 1 KB per warp request
+struct __align__(32) V32 {
+    unsigned long long a, b, c, d;
+};
+__device__ __forceinline__ V32 ld_src_v32(const V32 *p) {
+    V32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_peer_v32(V32 *p, const V32 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a),
+                 "l"(v.b), "l"(v.c), "l"(v.d)
+                 : "memory");
+}
+__device__ int g_a2a_vec32 = 0;   // set from PB200_A2A_VEC32 (experiment knob)
+
 // contiguous copy of n 16 B units: kA2AUnroll independent loads in flight per thread
 __device__ __forceinline__ void copy_linear16(int4 *__restrict__ dst, const int4 *__restrict__ src,
                                               long long n) {
-    long long u = threadIdx.x;
     const long long step = kA2AThreads;
+    if (g_a2a_vec32 && ((((unsigned long long)dst | (unsigned long long)src) & 31ull) == 0)) {
+        const long long n2 = n >> 1;
+        V32 *d2 = (V32 *)dst;
+        const V32 *s2 = (const V32 *)src;
+        long long u = threadIdx.x;
+        constexpr int UN = kA2AUnroll / 2;
+        for (; u + (UN - 1) * step < n2; u += UN * step) {
+            V32 v[UN];
+#pragma unroll
+            for (int k = 0; k < UN; ++k) v[k] = ld_src_v32(s2 + u + k * step);
+#pragma unroll
+            for (int k = 0; k < UN; ++k) st_peer_v32(d2 + u + k * step, v[k]);
+        }
+        for (; u < n2; u += step) st_peer_v32(d2 + u, ld_src_v32(s2 + u));
+        if ((n & 1) && threadIdx.x == 0) st_peer_v4(dst + n - 1, ld_src_v4(src + n - 1));
+        return;
+    }
+    long long u = threadIdx.x;
     for (; u + (kA2AUnroll - 1) * step < n; u += kA2AUnroll * step) {
         int4 v[kA2AUnroll];
 #pragma unroll
@@ -155,7 +190,7 @@ __device__ __forceinline__ void copy_units(unsigned char *dst, long long dst_str
 
 __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) {
     __shared__ unsigned long long s_epoch;
-    __shared__ unsigned long long s_payload;
+    __shared__ long long s_dst_off[PB200_A2A_MAX_RANKS];
     const int W = a.world;
     const int me = a.rank;
     SignalPad *my_pad = a.peer_pad[me];
@@ -164,31 +199,32 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
     __syncthreads();
     const unsigned long long e = s_epoch;
 
-    // 1. ready: CTA 0 posts my receive offsets to every source
-    if (blockIdx.x == 0 && threadIdx.x < W && (int)threadIdx.x != me) {
-        SignalPad *pp = a.peer_pad[threadIdx.x];
-        st_relaxed_sys(&pp->ready_payload[me], (unsigned long long)a.recv_off[threadIdx.x]);
-        st_release_sys(&pp->ready_epoch[me], e);
+    // 1. ready: CTA 0 posts my receive offsets to every source; every CTA then collects the
+    //    destinations' offsets — one thread per destination, all flags polled concurrently
+    //    (the flags live in this rank's own pad: local memory reads).
+    if (threadIdx.x < W) {
+        const int r = threadIdx.x;
+        if (r == me) {
+            s_dst_off[r] = a.recv_off[me];
+        } else {
+            if (blockIdx.x == 0) {
+                SignalPad *pp = a.peer_pad[r];
+                st_relaxed_sys(&pp->ready_payload[me], (unsigned long long)a.recv_off[r]);
+                st_release_sys(&pp->ready_epoch[me], e);
+            }
+            const bool ok = wait_flag_ge(&my_pad->ready_epoch[r], e, a.spin_cycles, a.error);
+            // on timeout: never write to an unready peer
+            s_dst_off[r] = ok ? (long long)ld_relaxed_sys(&my_pad->ready_payload[r]) : -1;
+        }
     }
+    __syncthreads();
 
-    // 2. push
+    // 2. push: all destinations back to back, no barrier in between.  Order: self first, then
+    //    destinations staggered by rank and by CTA so every NVSwitch port is busy.
     for (int k = 0; k < W; ++k) {
-        // rotation: self first (no handshake needed, overlaps the ready round trip), then
-        // destinations staggered by rank and by CTA so every NVSwitch port is busy
         const int j = (k == 0) ? me : (me + 1 + ((k - 1) + blockIdx.x) % (W - 1)) % W;
         const PeerCopy pc = a.copy[j];
-        long long dst_off;
-        if (j == me) {
-            dst_off = a.recv_off[me];
-        } else {
-            if (threadIdx.x == 0) {
-                const bool ok = wait_flag_ge(&my_pad->ready_epoch[j], e, a.spin_cycles, a.error);
-                // on timeout: skip this destination (payload -1), never write to an unready peer
-                s_payload = ok ? ld_relaxed_sys(&my_pad->ready_payload[j]) : ~0ull;
-            }
-            __syncthreads();
-            dst_off = (long long)s_payload;
-        }
+        const long long dst_off = s_dst_off[j];
         if (pc.rows > 0 && pc.run_bytes > 0 && dst_off >= 0) {
             unsigned char *dst = a.peer_data[j] + dst_off;
             // copy unit from the alignment of everything that moves for THIS destination (the
@@ -220,29 +256,36 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
                     copy_units<1>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
             }
         }
-        // 3. done: last CTA for this destination signals it
-        __syncthreads();
-        if (threadIdx.x == 0 && j != me) {
+    }
+
+    // 3. done: one barrier, then W threads signal their destination in parallel — the last CTA to
+    //    finish (device-scope counter) releases the flag; fence.acq_rel.sys orders this CTA's
+    //    peer stores (all threads, via the barrier) before the counter / flag.
+    __syncthreads();
+    if (threadIdx.x < W && (int)threadIdx.x != me) {
+        const int j = threadIdx.x;
+        __threadfence_system();
+        const unsigned prev = atomicAdd(&a.peer_cnt[j], 1u);
+        if (prev == gridDim.x - 1) {
+            a.peer_cnt[j] = 0;
             __threadfence_system();
-            const unsigned prev = atomicAdd(&a.peer_cnt[j], 1u);
-            if (prev == gridDim.x - 1) {
-                a.peer_cnt[j] = 0;
-                __threadfence_system();
-                st_release_sys(&a.peer_pad[j]->done_epoch[me], e);
-            }
+            st_release_sys(&a.peer_pad[j]->done_epoch[me], e);
         }
     }
 
-    // 4. wait: last CTA of the grid waits for all sources, then publishes the epoch
+    // 4. wait: the last CTA of the grid waits for all sources (in parallel), then publishes the epoch
+    __shared__ unsigned s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned prev = atomicAdd(a.grid_cnt, 1u);
-        if (prev == gridDim.x - 1) {
-            for (int r = 0; r < W; ++r) {
-                if (r == me) continue;
-                wait_flag_ge(&my_pad->done_epoch[r], e, a.spin_cycles, a.error);
-            }
+        s_last = (atomicAdd(a.grid_cnt, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < W && (int)threadIdx.x != me)
+            wait_flag_ge(&my_pad->done_epoch[threadIdx.x], e, a.spin_cycles, a.error);
+        __syncthreads();
+        if (threadIdx.x == 0) {
             *a.grid_cnt = 0;
             *(volatile unsigned long long *)a.epoch = e;
             __threadfence();
@@ -293,6 +336,9 @@ extern "C" int pb200_a2a_comm_create(pb200_a2a_comm **comm, int32_t rank, int32_
     c->spin_cycles = 20ll * 1000 * 1000 * 1000;  // ~10 s at 2 GHz
     const char *env = getenv("PB200_A2A_CTAS");
     c->max_ctas = env ? atoi(env) : 0;
+    const char *v32 = getenv("PB200_A2A_VEC32");
+    const int use32 = v32 ? atoi(v32) : 0;
+    cudaMemcpyToSymbol(g_a2a_vec32, &use32, sizeof(int));
     *comm = c;
     return PB200_OK;
 }
@@ -331,8 +377,8 @@ static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, c
     a.spin_cycles = c->spin_cycles;
     a.rank = c->rank;
     a.world = c->world;
-    // grid: one CTA per 64 KB of the largest per-peer block, at least 1, at most the SM count
-    long long grid = (max_peer_bytes + (64ll << 10) - 1) / (64ll << 10);
+    // grid: one CTA per 16 KB of the largest per-peer block, at least 1, at most the SM count
+    long long grid = (max_peer_bytes + (16ll << 10) - 1) / (16ll << 10);
     const int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
