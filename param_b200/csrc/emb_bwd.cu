@@ -286,7 +286,12 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, 
                 for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(colp[c] + goff);
             }
             const bool all_valid = (j0 + U <= valid) && (j0 + U <= G);
-            if (!SIDE && all_valid && kk[0] == kk[U - 1] && (kk[0] == cur_key || cur_key == 0xffffffffu)) {
+            // every key of the batch must match (the sort may be on the low key bits only, so
+            // first == last does not imply the ones in between are equal)
+            bool same = true;
+#pragma unroll
+            for (int u = 1; u < U; ++u) same &= (kk[u] == kk[0]);
+            if (!SIDE && all_valid && same && (kk[0] == cur_key || cur_key == 0xffffffffu)) {
                 cur_key = kk[0];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
