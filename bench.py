@@ -129,6 +129,7 @@ def ev_time(fn, iters, stream=None):
     """CUDA-event time of `iters` back-to-back calls of fn on the current stream -> ms per call."""
     st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()                       # one untimed call: first-use allocations, lazy module loads
     torch.cuda.synchronize()
     e0.record(st)
     for _ in range(iters):

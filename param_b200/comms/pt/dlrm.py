@@ -135,7 +135,7 @@ class DLRMParallelEmbedding:
 
     def __init__(self, group, table_rows: Sequence[int], emb_dim: int, local_batch: int,
                  max_bag: int, device: torch.device, lr: float = 0.0, seed: int = 0,
-                 window: Optional[PeerWindow] = None, bwd_algo: str = "atomic"):
+                 window: Optional[PeerWindow] = None, bwd_algo: str = "sorted"):
         self.group, self.device = group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.table_rows = [int(r) for r in table_rows]
