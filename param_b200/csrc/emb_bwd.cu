@@ -211,12 +211,12 @@ __device__ __forceinline__ void add2b(float &a0, float &a1, float b0, float b1) 
 }
 
 template <int G, int C, bool SIDE>
-__global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, long long n,
-                                                             long long chunk_row0,
-                                                             const unsigned *__restrict__ keys,
-                                                             const unsigned *__restrict__ vals,
-                                                             const unsigned *__restrict__ goff_of,
-                                                             const float *__restrict__ w_of) {
+__device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long long n,
+                                                    long long chunk_row0,
+                                                    const unsigned *__restrict__ keys,
+                                                    const unsigned *__restrict__ vals,
+                                                    const unsigned *__restrict__ goff_of,
+                                                    const float *__restrict__ w_of, int seg_len) {
     constexpr int BPW = 32 / G;
     constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
     const int lane = threadIdx.x & 31;
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, 
     const int grp = lane / G;
     const int vec4 = p.dim >> 2;
     const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
-    const long long s0 = seg * kSeg;
-    const long long s1 = min(s0 + (long long)kSeg, n);
+    const long long s0 = seg * seg_len;
+    const long long s1 = min(s0 + (long long)seg_len, n);
     const int my_n = (s0 < n) ? (int)(s1 - s0) : 0;
     const int max_n = (BPW == 1) ? my_n : __reduce_max_sync(0xffffffffu, my_n);
 
@@ -329,6 +329,28 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, 
     flush();
 }
 
+template <int G, int C, bool SIDE>
+__global__ void __launch_bounds__(256) segment_reduce_kernel(const BwdParams p, long long n,
+                                                             long long chunk_row0,
+                                                             const unsigned *__restrict__ keys,
+                                                             const unsigned *__restrict__ vals,
+                                                             const unsigned *__restrict__ goff_of,
+                                                             const float *__restrict__ w_of,
+                                                             int seg_len) {
+    segment_reduce_body<G, C, SIDE>(p, n, chunk_row0, keys, vals, goff_of, w_of, seg_len);
+}
+// same body compiled for 4 resident CTAs/SM (64 registers): selectable with PB200_SEG_OCC4=1
+template <int G, int C, bool SIDE>
+__global__ void __launch_bounds__(256, 4) segment_reduce_kernel_occ4(const BwdParams p, long long n,
+                                                                     long long chunk_row0,
+                                                                     const unsigned *__restrict__ keys,
+                                                                     const unsigned *__restrict__ vals,
+                                                                     const unsigned *__restrict__ goff_of,
+                                                                     const float *__restrict__ w_of,
+                                                                     int seg_len) {
+    segment_reduce_body<G, C, SIDE>(p, n, chunk_row0, keys, vals, goff_of, w_of, seg_len);
+}
+
 static int bits_for(unsigned long long n) {
     int b = 1;
     while (b < 32 && (1ull << b) < n) ++b;
@@ -390,6 +412,15 @@ template <typename index_t>
 static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes, cudaStream_t st) {
     const bool side = (p.psw != nullptr) || p.mean;
     const int T = p.num_tables;
+    static const int seg_len = [] {
+        const char *e = getenv("PB200_SEG");   // sorted entries per lane group
+        const int v = e ? atoi(e) : kSeg;
+        return v >= 8 ? v : kSeg;
+    }();
+    static const int seg_occ4 = [] {
+        const char *e = getenv("PB200_SEG_OCC4");
+        return e ? atoi(e) : 0;
+    }();
     static const int sort_bits = [] {
         const char *e = getenv("PB200_SORT_BITS");   // 0 = full key; default 16 (two radix passes)
         return e ? atoi(e) : 16;
@@ -469,17 +500,20 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
             count_launch(4);  // onesweep: histogram + scan + digit passes (library kernels)
             const unsigned *ks = dk.Current();
             const unsigned *vs = dv.Current();
-            const long long n_seg = (n + kSeg - 1) / kSeg;
+            const long long n_seg = (n + seg_len - 1) / seg_len;
 #define PB200_SEG_LAUNCH(G_, C_)                                                                \
     do {                                                                                        \
         const long long per_block = 8ll * (32 / G_);                                            \
         const long long g2 = (n_seg + per_block - 1) / per_block;                               \
         if (side)                                                                               \
             segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, st>>>(                  \
-                p, n, row0, ks, vs, bag_of, w_of);                                              \
+                p, n, row0, ks, vs, bag_of, w_of, seg_len);                                     \
+        else if (seg_occ4)                                                                      \
+            segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(            \
+                p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
         else                                                                                    \
             segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(                 \
-                p, n, row0, ks, vs, nullptr, nullptr);                                          \
+                p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
     } while (0)
             if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
             else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);

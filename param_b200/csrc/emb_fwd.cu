@@ -18,6 +18,8 @@
 //            staged into shared memory with cp.async.bulk (TMA unit, UBLKCP) on an mbarrier by a
 //            producer warp running kStages tiles ahead, so the offsets -> indices -> rows
 //            dependency chain is off the consumers' critical path.
+#include <stdlib.h>
+
 #include "emb_core.cuh"
 
 namespace pb200 {
@@ -26,7 +28,7 @@ namespace pb200 {
 // DIRECT variant
 // ------------------------------------------------------------------------------------
 template <typename index_t, int G, int C, bool WEIGHTED>
-__global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) {
+__device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     constexpr int BPW = 32 / G;  // bags per warp
     constexpr int U = UnrollFor<C>::value;
     const int lane = threadIdx.x & 31;
@@ -55,6 +57,16 @@ __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) 
                             WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen, maxlen,
                             lane_g, vec4);
     if (active) acc.store(p, t, b, len, lane_g, vec4);
+}
+
+template <typename index_t, int G, int C, bool WEIGHTED>
+__global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) {
+    tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
+}
+// same body compiled for 5 resident CTAs/SM (48 registers): selectable with PB200_FWD_OCC5=1
+template <typename index_t, int G, int C, bool WEIGHTED>
+__global__ void __launch_bounds__(256, 5) tbe_fwd_direct_kernel_occ5(const FwdParams p) {
+    tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
 }
 
 // ------------------------------------------------------------------------------------
@@ -388,8 +400,14 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
         const long long bags_per_block = (long long)warps_per_block * BPW;
         const long long grid = (p.n_bags + bags_per_block - 1) / bags_per_block;
         if (grid > 0x7fffffffll) return PB200_EUNSUPPORTED;
+        static const int occ5 = [] {
+            const char *e = getenv("PB200_FWD_OCC5");
+            return e ? atoi(e) : 0;
+        }();
         if (weighted)
             tbe_fwd_direct_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
+        else if (occ5)
+            tbe_fwd_direct_kernel_occ5<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
         else
             tbe_fwd_direct_kernel<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
     }

@@ -199,3 +199,65 @@ def test_sparse_redistribution_plan_two_ranks_gloo(oracle, tmp_path):
                 starts.append(data[s][f"off{g}"] + base)
                 base += data[s][f"idx{g}"].size
             assert np.array_equal(offsets[f * W * b:(f + 1) * W * b] - lo, np.concatenate(starts))
+
+
+# ---- et_replay hooks against the real reference package (CPU, skipped when it is absent) -------
+def _et_replay_importable():
+    if not REF.exists():
+        return False
+    import types
+    sys.dont_write_bytecode = True
+    if str(REF) not in sys.path:
+        sys.path.insert(0, str(REF))
+    for name, attrs in (("pydot", ["Dot", "Node", "Edge", "Cluster"]), ("intervaltree", ["Interval", "IntervalTree"])):
+        if name not in sys.modules:              # absent third-party deps of et_replay
+            m = types.ModuleType(name)
+            for a in attrs:
+                setattr(m, a, type(a, (), {}))
+            sys.modules[name] = m
+    return True
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_et_replay_builds_b200_ops_from_name_and_schema():
+    """et_replay re-creates compute nodes from node.name + node.op_schema
+    (et_replay/et_replay_utils.py:129-212); the b200:: ops registered by `import param_b200.et`
+    (what the replay config's "import modules" does) must build through that exact function."""
+    assert _et_replay_importable()
+    import json
+    import types
+    from et_replay import et_replay_utils
+    cfg = json.loads((ROOT / "param_b200" / "et" / "replay-config-b200.json").read_text())
+    assert cfg["import modules"] == ["param_b200.et"]
+    for mod in cfg["import modules"]:
+        __import__(mod)
+    schemas = {
+        "b200::embedding_bag": ("b200::embedding_bag(Tensor weight, Tensor indices, Tensor offsets, int mode, "
+                                "Tensor? per_sample_weights, bool include_last_offset) -> Tensor", 6, 1),
+        "b200::tbe_forward": ("b200::tbe_forward(Tensor weights, Tensor row_offsets, int dim, Tensor indices, "
+                              "Tensor offsets, int batch, int mode, Tensor? per_sample_weights, int layout) -> Tensor", 9, 1),
+        "b200::regroup_sparse": ("b200::regroup_sparse(Tensor lengths, Tensor indices, int world, int tables_local, "
+                                 "int local_batch) -> (Tensor, Tensor, Tensor)", 5, 3),
+    }
+    for name, (schema, n_in, n_out) in schemas.items():
+        # the schema string must be the one the dispatcher really holds (what an ET capture records)
+        op = getattr(torch.ops.b200, name.split("::")[1])
+        assert str(op.default._schema).replace(" ", "") == schema.replace(" ", ""), name
+        node = types.SimpleNamespace(name=name, op_schema=schema, id=1,
+                                     input_types=["x"] * n_in, output_types=["y"] * n_out)
+        func, out_count = et_replay_utils.build_torchscript_func(node)
+        assert func is not None and out_count == n_out, name
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_et_replay_comm_backend_registers():
+    assert _et_replay_importable()
+    import inspect
+    from et_replay.comm.backend import base_backend
+    from param_b200.et.backend import B200ETStandalone, register_et_backend
+    cls = register_et_backend("b200")
+    assert base_backend.customized_backend["b200"] is cls and not inspect.isabstract(cls)
+    missing = [n for n in base_backend.BaseBackend.__abstractmethods__ if not callable(getattr(B200ETStandalone, n, None))]
+    assert not missing, missing
+    from param_b200.comms.pt.backend import B200CommsMixin
+    assert cls.all_to_allv is B200CommsMixin.all_to_allv     # replayed alltoall_base lands on the push kernel
