@@ -104,6 +104,7 @@ int pb200_embbag_fwd(const float *weight, int64_t num_rows, int32_t dim,
  *
  * T tables share one fp32 arena: table t occupies rows
  * [table_row_offsets[t], table_row_offsets[t+1]) of `weights` ([sum rows, dim]).
+ * The arena must hold fewer than 2^32 rows (row ids are 32-bit inside the kernels).
  * indices = cat_t(indices_t) (table-major), offsets int[T*B + 1] cumulative over
  * the concatenation, bag (t, b) = offsets[t*B + b .. t*B + b + 1).
  * Output element (t, b, d) is written at out[t*out_stride_t + b*out_stride_b + d]:

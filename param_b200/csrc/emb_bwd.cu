@@ -422,8 +422,8 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         return e ? atoi(e) : 0;
     }();
     static const int sort_bits = [] {
-        const char *e = getenv("PB200_SORT_BITS");   // 0 = full key; default 16 (two radix passes)
-        return e ? atoi(e) : 16;
+        const char *e = getenv("PB200_SORT_BITS");   // 0 = full key (default); 16 = two radix passes
+        return e ? atoi(e) : 0;
     }();
     SortedPlan pl = plan_sorted(p.n_indices, T, true);
     const long long need = (long long)pl.total_bytes + 256 + (long long)(T + 1) * 8;

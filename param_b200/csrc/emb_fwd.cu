@@ -489,9 +489,9 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
     p.has_last_offset = 1;
     p.mean = pool_mode == PB200_POOL_MEAN;
     cudaStream_t st = (cudaStream_t)stream;
-    // the arena row id must fit 32 bits for the vector path; the caller's arena is bounded by
-    // HBM (180 GB / 16 B min row = 1.1e10), so check the real bound on the host side: unknown
-    // here without a D2H read, hence the wrapper passes rows through n/a -> assume < 2^32.
+    // Contract (param_b200.h): the arena holds fewer than 2^32 rows — arena row ids are 32-bit inside
+    // the kernels.  table_row_offsets lives on the device, so the bound is the caller's to keep
+    // (ops.TableArena.allocate enforces it; 180 GB of HBM / 512 B rows is 3.5e8).
     if (idx_type == PB200_IDX_I64) return dispatch_fwd<long long>(p, algo, 0, st);
     if (idx_type == PB200_IDX_I32) return dispatch_fwd<int>(p, algo, 0, st);
     return PB200_EINVAL;
