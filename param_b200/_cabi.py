@@ -52,6 +52,17 @@ def load():
     if _lib is not None:
         return _lib
     if not _LIB_PATH.exists():
+        # a fresh checkout: compile the CUDA sources in-tree if a toolchain is present
+        # (this builds the same sm_100a library; it is not a fallback to another code path)
+        try:
+            from . import build as _build
+            _build.build_cuda()
+        except Exception as exc:  # noqa: BLE001
+            raise PB200Error(
+                f"{_LIB_PATH} not found and building it failed ({exc}); build it with "
+                "`python -m param_b200.build` (there is no CPU or PyTorch fallback for the "
+                "param_b200 kernels)") from exc
+    if not _LIB_PATH.exists():
         raise PB200Error(
             f"{_LIB_PATH} not found: build it with `python -m param_b200.build` "
             "(there is no CPU or PyTorch fallback for the param_b200 kernels)"

@@ -10,7 +10,7 @@
 // ATOMIC : one lane group per bag; the bag's gradient row is read once (16 B per lane) and
 //          red.global.add.v4.f32 is issued per lookup.  Summation order across bags is not fixed.
 // SORTED : per chunk of tables — (1) build (arena row, bag) pairs, (2) cub radix sort by row,
-//          (3) one lane group per 64 sorted entries accumulates runs of equal rows in registers and
+//          (3) one lane group per 128 sorted entries accumulates runs of equal rows in registers and
 //          issues ONE red per (segment, row).  Under Zipf skew ~87 % of the lookups of a table-batch
 //          are duplicates, so the number of L2 read-modify-writes drops ~8x and hot rows no longer
 //          serialise on one L2 slice; rows wholly inside a segment are updated exactly once
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) build_pairs_kernel(const BwdParams p, lon
 // entries alias gradient row 0 and are masked); a batch whose first and last key equal the running
 // key — the common case under skew, where one hot row spans thousands of entries — is added without
 // any per-entry bookkeeping.  Each (segment, row) ends in ONE red.global.add.v4.f32.
-constexpr int kSeg = 64;
+constexpr int kSeg = 128;  // measured: 128 beats 64 by 4.5 % under Zipf, costs 1.6 % under uniform indices
 
 __device__ __forceinline__ void add2b(float &a0, float &a1, float b0, float b1) {
     asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; "
