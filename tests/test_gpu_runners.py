@@ -1,0 +1,58 @@
+"""The stand-alone runners (mirrors of the reference CLIs) end to end on ONE GPU, each in its own
+process with WORLD_SIZE=1: the compute driver (config 1 plumbing on the GPU), the all-to-all sweep
+through B200Backend with the position-coded data check, and the DLRM pattern runner."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _run(args, port):
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(port), PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, *args], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_compute_driver_config1(cuda_device):
+    """config 1: single-table EmbeddingBag 1M x 64, batch 512, bag 20 through the op driver"""
+    out = _run(["-m", "param_b200.compute.pt.pytorch_emb", "--features", "1000000", "--embdim", "64",
+                "--nnz", "20", "--batch", "512", "--steps", "20", "--warmups", "3", "-d", "gpu"], 29701)
+    row = [ln for ln in out.splitlines() if ln.strip().startswith("1000000")]
+    assert len(row) == 1 and float(row[0].split(",")[-1]) > 0.0          # BW(GB/s) column
+    out = _run(["-m", "param_b200.compute.pt.driver", "--steps", "5", "--warmups", "2", "--device", "gpu",
+                "emb", "--dataset", "cfg1", "--alpha", "1.15", "--fast-indices"], 29702)
+    assert "with emb dataset  cfg1" in out and "1000000" in out
+
+
+@pytest.mark.parametrize("collective", ["all_to_all_single", "all_to_allv", "all_to_all"])
+def test_comms_sweep_world1(cuda_device, collective):
+    out = _run(["-m", "param_b200.comms.pt.comms", "--collective", collective, "--begin-size", "1K",
+                "--end-size", "4M", "--step-factor", "8", "--num-iters", "3", "--num_warmup_iters", "1",
+                "--check-data", "1", "--backend", "b200", "--json"], 29703)
+    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith("{")]
+    assert len(recs) == 5 and all(r["check"] == "PASS" and r["collective"] == collective for r in recs)
+
+
+def test_comms_sweep_cuda_graph_world1(cuda_device):
+    out = _run(["-m", "param_b200.comms.pt.comms", "--collective", "all_to_all_single", "--begin-size", "64K",
+                "--end-size", "64K", "--num-iters", "4", "--num_warmup_iters", "1", "--check-data", "1",
+                "--graph-launches", "2", "--backend", "b200", "--json"], 29704)
+    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith("{")]
+    assert len(recs) == 1 and recs[0]["check"] == "PASS"
+
+
+def test_dlrm_pattern_runner_world1(cuda_device):
+    out = _run(["-m", "param_b200.comms.pt.dlrm", "--mini-batch-size", "256", "--num-batches", "3",
+                "--warmup-batches", "1", "--arch-embedding-size", "5000x6", "--arch-sparse-feature-size", "64",
+                "--num-indices-per-lookup", "8", "--num-indices-per-lookup-fixed", "false", "--lr", "0.01",
+                "--json"], 29705)
+    rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+    assert rec["iter_time_ms_p50_max_rank"] > 0 and "offset_idx_xchg_ms_p50_max_rank" in rec
