@@ -146,8 +146,8 @@ class B200CommsMixin:
         need = out.numel() * out.element_size()
         if win.offset_of(out) is None and need > win.window_bytes:
             win = self._ensure_window(group, need)
-        if out.dtype != inp.dtype:      # et_replay's all_to_allv casts on mismatch (:350-356)
-            out = out.to(inp.dtype)
+        if out.dtype != inp.dtype:
+            raise PB200Error("all_to_all needs input and output of one dtype")
         win.all_to_all_single(out, inp.contiguous().view(-1),
                               list(out_splits) if out_splits is not None and len(out_splits) else None,
                               list(in_splits) if in_splits is not None and len(in_splits) else None)
@@ -171,6 +171,11 @@ class B200CommsMixin:
         ip = collectiveArgs.ipTensor if not pair else collectiveArgs.ipTensor_pair[pairIdx]
         osp = collectiveArgs.opTensor_split if not pair else collectiveArgs.opTensor_split_pair[pairIdx]
         isp = collectiveArgs.ipTensor_split if not pair else collectiveArgs.ipTensor_split_pair[pairIdx]
+        if not pair and op.dtype != ip.dtype:
+            # et_replay re-types the holder's output tensor on a dtype mismatch
+            # (et_replay/comm/backend/pytorch_dist_backend.py:350-356)
+            logger.warning("all_to_allv: opTensor and ipTensor are not the same dtype")
+            collectiveArgs.opTensor = op = op.to(ip.dtype)
         work = self._a2a(op, ip, osp, isp, collectiveArgs.group, collectiveArgs.asyncOp)
         if collectiveArgs.asyncOp:
             collectiveArgs.waitObj.append(work)
