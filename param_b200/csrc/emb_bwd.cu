@@ -468,7 +468,11 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
     int t0 = 0;
     while (t0 < T) {
         int t1 = t0 + 1;
-        while (t1 < T && h_bounds[t1 + 1] - h_bounds[t0] <= pl.max_pairs) ++t1;
+        // grow the chunk while its lookups fit the scratch AND its rows fit 24 key bits: the radix
+        // sort then needs 3 passes instead of 4 (measured: 1/4 of the sort time at 48 tables/chunk)
+        while (t1 < T && h_bounds[t1 + 1] - h_bounds[t0] <= pl.max_pairs &&
+               h_rows[t1 + 1] - h_rows[t0] <= (1ll << 24))
+            ++t1;
         const long long i_lo = h_bounds[t0], i_hi = h_bounds[t1];
         const long long n = i_hi - i_lo;
         if (n > pl.max_pairs) return PB200_EUNSUPPORTED;  // one table larger than the scratch plan
