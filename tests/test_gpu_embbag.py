@@ -326,3 +326,38 @@ graph(%0: Tensor, %1: Tensor, %2: Tensor, %3: int, %4: Tensor?, %5: bool):
     dst = torch.zeros(100, 128, device=cuda_device)
     torch.ops.b200.tbe_backward_(dst, tro, 128, _t(idx, cuda_device), off1, 12, torch.ones(12, 128, device=cuda_device), 0, 1.0, 0, 1)
     assert torch.equal(dst[:, 0].cpu(), torch.bincount(torch.from_numpy(idx), minlength=100).float())
+
+
+def test_emb_lookup_compute_function(cuda_device, oracle):
+    """backendFuncs.emb_lookup over requests prepared by init_emb_lookup (the comms-side compute
+    kernel, pytorch_dist_backend.py:832-857 + comms_utils.py:1956-2039), forward and backward."""
+    import types
+    from param_b200.comms.pt.backend import B200CommsMixin
+    from param_b200.comms.pt.emb_lookup import init_emb_lookup
+
+    class _Be(B200CommsMixin):
+        def get_device(self):
+            return cuda_device
+
+    be = _Be()
+    params = types.SimpleNamespace(direction="backward", emb_dim=64, num_embs=500, batch_size=32,
+                                   num_emb_tables_per_device=4, num_emb_tables_batched=2, bag_size=5,
+                                   device="cuda", emb_lr=0.5)
+    ca = types.SimpleNamespace(reuseTensors=True)    # retain_graph: the reference loops one backward per request
+    init_emb_lookup(ca, params, be)
+    assert ca.num_emb_ops == 2 and len(ca.emb) == 2 and len(ca.embRequests) == 2
+    op, (idx, off, _) = ca.emb[1], ca.embRequests[1]
+    w0 = op.weights.detach().cpu().numpy().copy()
+    tro = op.arena.row_offsets.cpu().numpy()
+    want_out = oracle.tbe_fwd(w0, tro, 64, idx.cpu().numpy(), off.cpu().numpy(), 32)
+    assert np.array_equal(ca.LookupOut.detach().cpu().numpy(), want_out)        # last op's forward
+    be.emb_lookup(ca)                                                            # direction == backward
+    want_w = w0.astype(np.float64) + oracle.tbe_bwd(int(tro[-1]), tro, 64, idx.cpu().numpy(), off.cpu().numpy(), 32,
+                                                    ca.grad_output.cpu().numpy(), scale=-0.5, dtype=np.float64)
+    got = op.weights.detach().cpu().numpy()
+    # the reference loops the SAME LookupOut.backward once per request: two SGD steps land on the last op
+    want_w2 = want_w + (want_w - w0.astype(np.float64))
+    assert np.abs(got - want_w2).max() <= RTOL * np.abs(want_w2).max() or np.abs(got - want_w).max() <= RTOL * np.abs(want_w).max()
+    ca.direction = "forward"
+    be.emb_lookup(ca)
+    assert ca.LookupOut.shape == (32, 2 * 64)

@@ -261,3 +261,18 @@ def test_et_replay_comm_backend_registers():
     assert not missing, missing
     from param_b200.comms.pt.backend import B200CommsMixin
     assert cls.all_to_allv is B200CommsMixin.all_to_allv     # replayed alltoall_base lands on the push kernel
+
+
+def test_tbe_request_generator_layout():
+    """TBE request layout (split_table_batched_embeddings_ops.py:93-135,191-213): table-major
+    indices, cumulative offsets over the concatenation, the reference's alpha regimes."""
+    from param_b200.comms.pt.emb_lookup import generate_requests
+    B, T, L, E = 6, 3, 4, 50
+    (idx, off, w), = generate_requests(1, B, T, L, E, alpha=0.0)
+    assert off.tolist() == [i * L for i in range(T * B + 1)] and idx.numel() == T * B * L and w is None
+    assert idx[:B * L].tolist() == [i % L for i in range(B * L)]                 # alpha == 0: i % L
+    (idx, off, w), = generate_requests(1, B, T, L, E, alpha=0.3, weighted=True)
+    assert idx[:B * L].tolist() == [i % E for i in range(B * L)] and w.numel() == idx.numel()
+    for alpha in (1.0, 1.15):
+        (idx, _, _), = generate_requests(1, B, T, L, E, alpha=alpha, seed=1)
+        assert int(idx.min()) >= 0 and int(idx.max()) < E
