@@ -1,0 +1,78 @@
+"""Operator plugin for the reference's config-driven micro-benchmark framework
+(train/compute/python): an object with the OperatorInterface protocol —
+build / cleanup / forward / create_grad / backward (lib/operator.py:8-45) — wrapping the B200
+batched EmbeddingBag, with the build() signature of the fbgemm wrapper it stands in for
+(workloads/pytorch/split_table_batched_embeddings_ops.py:248-303) so that the same JSON op configs
+drive it.  `register()` puts it into the reference's op_map (lib/operator.py:48-68) when that
+package is importable; the class itself has no dependency on it (OperatorInterface accepts any
+class with a callable `forward` through __subclasshook__, :18-24).
+"""
+from __future__ import annotations
+
+from typing import List, Union
+
+import torch
+
+from .._cabi import PB200Error
+from .tbe import B200TBE
+
+OP_NAME = "B200BatchedEmbeddingBag"
+
+
+class B200BatchedEmbeddingBagOp:
+    def __init__(self) -> None:
+        self.device = None          # set by the framework before build() (lib/operator.py:26-27)
+        self.op = None
+        self.fwd_out = None
+        self.grad_in = None
+
+    def build(self, num_tables: int, rows: Union[int, List[int]], dims: Union[int, List[int]],
+              pooling: int = 0, weighted: bool = False, weights_precision: str = "fp32",
+              optimizer: str = "exact_sgd", lr: float = 0.01, eps: float = 1.0e-8,
+              weight_decay: float = 0.0, weight_decay_mode=None) -> None:
+        dev = str(self.device or "cuda")
+        if not dev.startswith("cuda"):
+            raise PB200Error(f"{OP_NAME} runs on CUDA devices only (got {dev})")
+        if weights_precision not in ("fp32", "float32"):
+            raise PB200Error("B200 tables are fp32")
+        rows_list = rows if isinstance(rows, list) else [rows] * num_tables
+        dims_list = dims if isinstance(dims, list) else [dims] * num_tables
+        if len(rows_list) == 1:
+            rows_list = rows_list * num_tables
+        if len(dims_list) == 1:
+            dims_list = dims_list * num_tables
+        mode = {0: "sum", 1: "mean"}.get(int(pooling))      # fbgemm PoolingMode: SUM = 0, MEAN = 1
+        if mode is None:
+            raise PB200Error("pooling must be 0 (sum) or 1 (mean)")
+        self.weighted = bool(weighted)
+        self.op = B200TBE(list(zip(rows_list, dims_list)), lr=lr, pooling_mode=mode,
+                          device=torch.device(dev))
+
+    def cleanup(self) -> None:
+        self.op = self.fwd_out = self.grad_in = None
+
+    def forward(self, *args, **kwargs):
+        indices, offsets = args[0], args[1]
+        psw = args[2] if len(args) > 2 else None
+        self.fwd_out = self.op.forward(indices, offsets, psw)
+        return self.fwd_out
+
+    def create_grad(self) -> None:
+        self.grad_in = torch.ones_like(self.fwd_out)
+
+    def backward(self, grad=None) -> None:
+        if grad is None:
+            if self.grad_in is None:
+                self.create_grad()
+            grad = self.grad_in
+        self.fwd_out.backward(grad)
+
+
+def register(name: str = OP_NAME):
+    """Add the op to the reference's global registry (needs `param_bench.train.compute.python`
+    importable).  Raises ValueError on a duplicate name, like the reference."""
+    from param_bench.train.compute.python.lib.operator import register_operator
+
+    op = B200BatchedEmbeddingBagOp()
+    register_operator(name, op)
+    return op

@@ -361,3 +361,24 @@ def test_emb_lookup_compute_function(cuda_device, oracle):
     ca.direction = "forward"
     be.emb_lookup(ca)
     assert ca.LookupOut.shape == (32, 2 * 64)
+
+
+def test_operator_plugin_runs(cuda_device, oracle):
+    """train/compute/python OperatorInterface protocol: build -> forward -> create_grad -> backward"""
+    from param_b200.comms.pt.emb_lookup import generate_requests
+    from param_b200.compute.operator import B200BatchedEmbeddingBagOp
+    op = B200BatchedEmbeddingBagOp()
+    op.device = str(cuda_device)
+    op.build(3, 400, 128, pooling=0, weighted=False, weights_precision="fp32", optimizer="exact_sgd", lr=0.1)
+    (idx, off, w), = generate_requests(1, 64, 3, 10, 400, alpha=1.15, seed=2, device=cuda_device)
+    w0 = op.op.weights.detach().cpu().numpy().copy()
+    tro = op.op.arena.row_offsets.cpu().numpy()
+    out = op.forward(idx, off, w)
+    assert np.array_equal(out.detach().cpu().numpy(), oracle.tbe_fwd(w0, tro, 128, idx.cpu().numpy(), off.cpu().numpy(), 64))
+    op.create_grad()
+    op.backward()
+    want = w0.astype(np.float64) + oracle.tbe_bwd(int(tro[-1]), tro, 128, idx.cpu().numpy(), off.cpu().numpy(), 64,
+                                                  np.ones((64, 3 * 128), np.float32), scale=-0.1, dtype=np.float64)
+    assert np.abs(op.op.weights.detach().cpu().numpy() - want).max() <= RTOL * np.abs(want).max()
+    op.cleanup()
+    assert op.op is None

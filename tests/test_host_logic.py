@@ -276,3 +276,26 @@ def test_tbe_request_generator_layout():
     for alpha in (1.0, 1.15):
         (idx, _, _), = generate_requests(1, B, T, L, E, alpha=alpha, seed=1)
         assert int(idx.min()) >= 0 and int(idx.max()) < E
+
+
+def test_operator_plugin_protocol():
+    """OperatorInterface protocol of train/compute/python (lib/operator.py:8-45)"""
+    from param_b200._cabi import PB200Error
+    from param_b200.compute.operator import B200BatchedEmbeddingBagOp
+    op = B200BatchedEmbeddingBagOp()
+    for name in ("build", "cleanup", "forward", "create_grad", "backward"):
+        assert callable(getattr(op, name))
+    op.device = "cpu"
+    with pytest.raises(PB200Error):
+        op.build(2, 100, 16)
+    if REF.exists():
+        from make_golden import _ref_paths
+        _ref_paths()
+        from param_bench.train.compute.python.lib import operator as ref_operator
+        assert issubclass(B200BatchedEmbeddingBagOp, ref_operator.OperatorInterface)   # __subclasshook__
+        from param_b200.compute import operator as plugin
+        name = "B200BatchedEmbeddingBag_test"
+        registered = plugin.register(name)
+        assert ref_operator.op_map[name] is registered
+        with pytest.raises(ValueError):
+            plugin.register(name)
