@@ -23,7 +23,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import time
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 

@@ -39,7 +39,6 @@ struct BwdParams {
     int num_tables;
     int dim;
     int mean;
-    long long total_rows_hint;
 };
 
 __device__ __forceinline__ void split_bag_bwd(const BwdParams &p, long long gb, int &t,
@@ -463,7 +462,7 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
     // gradient row offsets travel as 32-bit float4 indices
     {
         const long long last = (long long)(T - 1) * p.go_stride_t + (p.batch - 1) * p.go_stride_b + p.dim;
-        if ((last >> 2) >= 0xffffffffll || p.total_rows_hint >= 0xffffffffll) return PB200_EUNSUPPORTED;
+        if ((last >> 2) >= 0xffffffffll) return PB200_EUNSUPPORTED;
     }
     int t0 = 0;
     while (t0 < T) {

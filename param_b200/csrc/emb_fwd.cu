@@ -417,12 +417,12 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
 }
 
 template <typename index_t>
-static int dispatch_fwd(FwdParams &p, int algo, long long total_rows_hint, cudaStream_t st) {
+static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t st) {
     if (p.n_bags == 0) return PB200_OK;
     const bool vec_ok = (p.dim % 4 == 0) && (p.dim <= 512) &&
                         (((uintptr_t)p.weights & 15) == 0) && (((uintptr_t)p.out & 15) == 0) &&
                         (p.out_stride_t % 4 == 0) && (p.out_stride_b % 4 == 0) &&
-                        (total_rows_hint < (1ll << 32));
+                        (num_rows < (1ll << 32));
     if (!vec_ok) {
         const long long grid = (p.n_bags + 7) / 8;
         if (grid > 0x7fffffffll) return PB200_EUNSUPPORTED;

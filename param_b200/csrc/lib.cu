@@ -62,7 +62,6 @@ __device__ __forceinline__ long long zipf_draw(const double *__restrict__ cdf, l
 // One thread per bag.  dedupe != 0 reproduces the reference's "sampling without replacement per
 // bag" (pytorch_emb.py:146-157: oversample, keep the first nnz distinct values) — but keeps drawing
 // past 2*nnz instead of failing when a bag has fewer than nnz distinct values among them.
-constexpr int kMaxNnz = 128;
 __global__ void __launch_bounds__(128) fill_zipf_bags_kernel(long long *dst, long long n_bags,
                                                              int nnz,
                                                              const double *__restrict__ cdf,
