@@ -393,7 +393,7 @@ extern "C" int64_t pb200_tbe_bwd_scratch_bytes(int64_t n_indices, int32_t num_ta
     if (n_indices <= 0) return 0;
     // +table_bounds: (T+1) int64 host-mirrored lookup bounds are read back once per call
     SortedPlan pl = plan_sorted(n_indices, num_tables, true);
-    return (int64_t)pl.total_bytes + 256 + (int64_t)(num_tables + 1) * 8;
+    return 2 * (int64_t)pl.total_bytes + 256 + (int64_t)(num_tables + 1) * 8;   // two chunk sets
 }
 
 namespace pb200 {
@@ -406,6 +406,20 @@ __global__ void table_bounds_kernel(const index_t *offsets, long long batch, int
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t <= num_tables) out[t] = (long long)offsets[(long long)t * batch];
 }
+
+// Scratch for one chunk in flight; two sets let chunk i+1 be built and sorted (side stream) while
+// the segmented reduce of chunk i runs (caller's stream).
+struct SortSet {
+    void *cub_tmp;
+    unsigned *k0, *k1, *v0, *v1, *goff_of;
+    float *w_of;
+};
+
+struct SortedChunk {
+    int t0, t1;
+    long long i_lo, n, row0, row1, gb_lo, gb_hi;
+    const unsigned *ks, *vs;
+};
 
 template <typename index_t>
 static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes, cudaStream_t st) {
@@ -424,19 +438,27 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         const char *e = getenv("PB200_SORT_BITS");   // 0 = full key (default); 16 = two radix passes
         return e ? atoi(e) : 0;
     }();
+    static const int overlap = [] {
+        const char *e = getenv("PB200_BWD_OVERLAP");  // 1 (default): sort of chunk i+1 under reduce of chunk i
+        return e ? atoi(e) : 1;
+    }();
     SortedPlan pl = plan_sorted(p.n_indices, T, true);
-    const long long need = (long long)pl.total_bytes + 256 + (long long)(T + 1) * 8;
+    const long long need = 2 * (long long)pl.total_bytes + 256 + (long long)(T + 1) * 8;
     if (!scratch || scratch_bytes < need) return PB200_EINVAL;
     unsigned char *base = (unsigned char *)scratch;
-    size_t arr = ((size_t)pl.max_pairs * 4 + 255) & ~(size_t)255;
-    void *cub_tmp = base;
-    unsigned *k0 = (unsigned *)(base + pl.cub_bytes);
-    unsigned *k1 = (unsigned *)(base + pl.cub_bytes + arr);
-    unsigned *v0 = (unsigned *)(base + pl.cub_bytes + 2 * arr);
-    unsigned *v1 = (unsigned *)(base + pl.cub_bytes + 3 * arr);
-    unsigned *bag_of = (unsigned *)(base + pl.cub_bytes + 4 * arr);
-    float *w_of = (float *)(base + pl.cub_bytes + 5 * arr);
-    long long *d_bounds = (long long *)(base + pl.cub_bytes + 6 * arr);
+    const size_t arr = ((size_t)pl.max_pairs * 4 + 255) & ~(size_t)255;
+    SortSet sets[2];
+    for (int k = 0; k < 2; ++k) {
+        unsigned char *b0 = base + (size_t)k * pl.total_bytes;
+        sets[k].cub_tmp = b0;
+        sets[k].k0 = (unsigned *)(b0 + pl.cub_bytes);
+        sets[k].k1 = (unsigned *)(b0 + pl.cub_bytes + arr);
+        sets[k].v0 = (unsigned *)(b0 + pl.cub_bytes + 2 * arr);
+        sets[k].v1 = (unsigned *)(b0 + pl.cub_bytes + 3 * arr);
+        sets[k].goff_of = (unsigned *)(b0 + pl.cub_bytes + 4 * arr);
+        sets[k].w_of = (float *)(b0 + pl.cub_bytes + 5 * arr);
+    }
+    long long *d_bounds = (long long *)(base + 2 * pl.total_bytes);
 
     // table boundaries in lookup space and row space -> host (T+1 values each; tiny, one sync)
     table_bounds_kernel<index_t><<<(T + 1 + 127) / 128, 128, 0, st>>>((const index_t *)p.offsets,
@@ -464,53 +486,97 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         const long long last = (long long)(T - 1) * p.go_stride_t + (p.batch - 1) * p.go_stride_b + p.dim;
         if ((last >> 2) >= 0xffffffffll) return PB200_EUNSUPPORTED;
     }
-    int t0 = 0;
-    while (t0 < T) {
+
+    // ---- chunk plan (host) ----
+    static thread_local SortedChunk *chunks = nullptr;
+    static thread_local int chunks_cap = 0;
+    if (chunks_cap < T) {
+        free(chunks);
+        chunks = (SortedChunk *)malloc(sizeof(SortedChunk) * (size_t)T);
+        if (!chunks) return PB200_EINVAL;
+        chunks_cap = T;
+    }
+    int n_chunks = 0;
+    for (int t0 = 0; t0 < T;) {
         int t1 = t0 + 1;
         // grow the chunk while its lookups fit the scratch AND its rows fit 24 key bits: the radix
         // sort then needs 3 passes instead of 4 (measured: 1/4 of the sort time at 48 tables/chunk)
         while (t1 < T && h_bounds[t1 + 1] - h_bounds[t0] <= pl.max_pairs &&
                h_rows[t1 + 1] - h_rows[t0] <= (1ll << 24))
             ++t1;
-        const long long i_lo = h_bounds[t0], i_hi = h_bounds[t1];
-        const long long n = i_hi - i_lo;
-        if (n > pl.max_pairs) return PB200_EUNSUPPORTED;  // one table larger than the scratch plan
-        const long long row0 = h_rows[t0], row1 = h_rows[t1];
-        if (row1 - row0 > 0xffffffffll) return PB200_EUNSUPPORTED;
-        const long long gb_lo = (long long)t0 * p.batch, gb_hi = (long long)t1 * p.batch;
-        if (gb_hi - gb_lo > 0xffffffffll || n > 0x7fffffffll) return PB200_EUNSUPPORTED;
-        if (n > 0) {
-            const long long threads = (gb_hi - gb_lo) * 8;
-            const long long grid = (threads + 255) / 256;
-            if (grid > 0x7fffffffll) return PB200_EUNSUPPORTED;
-            if (side)
-                build_pairs_kernel<index_t, true><<<(unsigned)grid, 256, 0, st>>>(
-                    p, gb_lo, gb_hi, i_lo, row0, k0, v0, bag_of, w_of);
-            else
-                build_pairs_kernel<index_t, false><<<(unsigned)grid, 256, 0, st>>>(
-                    p, gb_lo, gb_hi, i_lo, row0, k0, v0, nullptr, nullptr);
-            count_launch();
-            PB200_LAUNCH_CHECK();
-            cub::DoubleBuffer<unsigned> dk(k0, k1), dv(v0, v1);
-            size_t tmp = pl.cub_bytes;
-            // Grouping, not ordering, is what the segmented reduce needs: sorting on the low
-            // `sort_bits` of the row id (stable) keeps equal rows adjacent except where two rows of
-            // one table share those bits — rare for the rows that matter (hot rows have distinct
-            // low bits) — and costs one radix pass less than a full-key sort.
-            int key_bits = bits_for((unsigned long long)(row1 - row0));
-            if (sort_bits > 0 && key_bits > sort_bits) key_bits = sort_bits;
-            PB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, dk, dv, (int)n, 0, key_bits, st));
-            count_launch(4);  // onesweep: histogram + scan + digit passes (library kernels)
-            const unsigned *ks = dk.Current();
-            const unsigned *vs = dv.Current();
-            const long long n_seg = (n + seg_len - 1) / seg_len;
+        SortedChunk c{};
+        c.t0 = t0;
+        c.t1 = t1;
+        c.i_lo = h_bounds[t0];
+        c.n = h_bounds[t1] - h_bounds[t0];
+        c.row0 = h_rows[t0];
+        c.row1 = h_rows[t1];
+        c.gb_lo = (long long)t0 * p.batch;
+        c.gb_hi = (long long)t1 * p.batch;
+        if (c.n > pl.max_pairs) return PB200_EUNSUPPORTED;  // one table larger than the scratch plan
+        if (c.row1 - c.row0 > 0xffffffffll) return PB200_EUNSUPPORTED;
+        if (c.gb_hi - c.gb_lo > 0xffffffffll || c.n > 0x7fffffffll) return PB200_EUNSUPPORTED;
+        if ((c.gb_hi - c.gb_lo) * 8 / 256 > 0x7fffffffll) return PB200_EUNSUPPORTED;
+        if (c.n > 0) chunks[n_chunks++] = c;
+        t0 = t1;
+    }
+    if (n_chunks == 0) return PB200_OK;
+
+    // ---- side stream + events (created once per host thread) ----
+    static thread_local cudaStream_t s2 = nullptr;
+    static thread_local cudaEvent_t ev_start = nullptr, ev_sorted[2] = {nullptr, nullptr},
+                                    ev_seg[2] = {nullptr, nullptr};
+    const bool use_overlap = overlap && n_chunks > 1;
+    if (use_overlap && !s2) {
+        PB200_CUDA_TRY(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_sorted[k], cudaEventDisableTiming));
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_seg[k], cudaEventDisableTiming));
+        }
+    }
+
+    // build (row, gradient offset) pairs of chunk c and sort them by row, on stream s
+    auto prepare = [&](int ci, cudaStream_t s) -> int {
+        SortedChunk &c = chunks[ci];
+        const SortSet &ss = sets[ci & 1];
+        const long long threads = (c.gb_hi - c.gb_lo) * 8;
+        const long long grid = (threads + 255) / 256;
+        if (side)
+            build_pairs_kernel<index_t, true><<<(unsigned)grid, 256, 0, s>>>(
+                p, c.gb_lo, c.gb_hi, c.i_lo, c.row0, ss.k0, ss.v0, ss.goff_of, ss.w_of);
+        else
+            build_pairs_kernel<index_t, false><<<(unsigned)grid, 256, 0, s>>>(
+                p, c.gb_lo, c.gb_hi, c.i_lo, c.row0, ss.k0, ss.v0, nullptr, nullptr);
+        count_launch();
+        PB200_LAUNCH_CHECK();
+        cub::DoubleBuffer<unsigned> dk(ss.k0, ss.k1), dv(ss.v0, ss.v1);
+        size_t tmp = pl.cub_bytes;
+        // Grouping, not ordering, is what the segmented reduce needs: PB200_SORT_BITS > 0 sorts on
+        // the low bits of the row id only (stable), one radix pass less at the price of more reds.
+        int key_bits = bits_for((unsigned long long)(c.row1 - c.row0));
+        if (sort_bits > 0 && key_bits > sort_bits) key_bits = sort_bits;
+        PB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ss.cub_tmp, tmp, dk, dv, (int)c.n, 0, key_bits, s));
+        count_launch(4);  // onesweep: histogram + scan + digit passes (library kernels)
+        c.ks = dk.Current();
+        c.vs = dv.Current();
+        return PB200_OK;
+    };
+
+    // segmented reduce of chunk c on the caller's stream
+    auto reduce = [&](int ci) -> int {
+        const SortedChunk &c = chunks[ci];
+        const SortSet &ss = sets[ci & 1];
+        const long long n = c.n, row0 = c.row0;
+        const unsigned *ks = c.ks, *vs = c.vs;
+        const long long n_seg = (n + seg_len - 1) / seg_len;
 #define PB200_SEG_LAUNCH(G_, C_)                                                                \
     do {                                                                                        \
         const long long per_block = 8ll * (32 / G_);                                            \
         const long long g2 = (n_seg + per_block - 1) / per_block;                               \
         if (side)                                                                               \
             segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, st>>>(                  \
-                p, n, row0, ks, vs, bag_of, w_of, seg_len);                                     \
+                p, n, row0, ks, vs, ss.goff_of, ss.w_of, seg_len);                              \
         else if (seg_occ4)                                                                      \
             segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(            \
                 p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
@@ -518,17 +584,45 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
             segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(                 \
                 p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
     } while (0)
-            if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
-            else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);
-            else if (vec4 <= 16) PB200_SEG_LAUNCH(16, 1);
-            else if (vec4 <= 32) PB200_SEG_LAUNCH(32, 1);
-            else if (vec4 <= 64) PB200_SEG_LAUNCH(32, 2);
-            else PB200_SEG_LAUNCH(32, 4);
+        if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
+        else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);
+        else if (vec4 <= 16) PB200_SEG_LAUNCH(16, 1);
+        else if (vec4 <= 32) PB200_SEG_LAUNCH(32, 1);
+        else if (vec4 <= 64) PB200_SEG_LAUNCH(32, 2);
+        else PB200_SEG_LAUNCH(32, 4);
 #undef PB200_SEG_LAUNCH
-            count_launch();
-            PB200_LAUNCH_CHECK();
+        count_launch();
+        PB200_LAUNCH_CHECK();
+        return PB200_OK;
+    };
+
+    if (!use_overlap) {
+        for (int ci = 0; ci < n_chunks; ++ci) {
+            int rc = prepare(ci, st);
+            if (rc != PB200_OK) return rc;
+            rc = reduce(ci);
+            if (rc != PB200_OK) return rc;
         }
-        t0 = t1;
+        return PB200_OK;
+    }
+
+    // software pipeline over chunks: prepare(i+1) on the side stream while reduce(i) runs on `st`
+    PB200_CUDA_TRY(cudaEventRecord(ev_start, st));          // inputs are ready at this point of `st`
+    PB200_CUDA_TRY(cudaStreamWaitEvent(s2, ev_start, 0));
+    int rc = prepare(0, st);
+    if (rc != PB200_OK) return rc;
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        if (ci + 1 < n_chunks) {
+            // set (ci+1)&1 was last read by reduce(ci-1): wait for it before overwriting
+            if (ci >= 1) PB200_CUDA_TRY(cudaStreamWaitEvent(s2, ev_seg[(ci + 1) & 1], 0));
+            rc = prepare(ci + 1, s2);
+            if (rc != PB200_OK) return rc;
+            PB200_CUDA_TRY(cudaEventRecord(ev_sorted[(ci + 1) & 1], s2));
+        }
+        if (ci >= 1) PB200_CUDA_TRY(cudaStreamWaitEvent(st, ev_sorted[ci & 1], 0));
+        rc = reduce(ci);
+        if (rc != PB200_OK) return rc;
+        PB200_CUDA_TRY(cudaEventRecord(ev_seg[ci & 1], st));
     }
     return PB200_OK;
 }
