@@ -299,3 +299,32 @@ def test_operator_plugin_protocol():
         assert ref_operator.op_map[name] is registered
         with pytest.raises(ValueError):
             plugin.register(name)
+
+
+def _payload_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    from param_b200.comms.pt.comms import _expected, _payload
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for dtype in (torch.float32, torch.int64, torch.uint8):
+        numel = 64 * world
+        x = _payload(rank, numel, dtype, "cpu")
+        out = torch.empty_like(x)
+        dist.all_to_all_single(out, x)
+        ok &= bool(torch.equal(out, _expected(rank, world, numel, dtype, "cpu")))
+        # a deliberately wrong permutation (blocks reversed) must be caught by the position code
+        wrong = torch.cat(list(reversed(out.split(numel // world))))
+        ok &= not bool(torch.equal(wrong, _expected(rank, world, numel, dtype, "cpu")))
+    Path(tmp, f"ok{rank}").write_text("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_position_coded_data_check_matches_c10d_two_ranks_gloo(tmp_path):
+    """the sweep's `--c 1` oracle (_payload/_expected) against a real c10d all_to_all_single, and its
+    power to detect a wrong permutation (the reference's constant-fill dcheck cannot)"""
+    import torch.multiprocessing as mp
+    mp.spawn(_payload_worker, args=(2, 29681, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").read_text() == "1" and (tmp_path / "ok1").read_text() == "1"
