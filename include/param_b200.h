@@ -55,6 +55,19 @@ extern "C" {
 #define PB200_BWD_AUTO 0
 #define PB200_BWD_ATOMIC 1 /* red.global.add.v4.f32 per lookup (order not fixed)       */
 #define PB200_BWD_SORTED 2 /* radix sort by row, segmented reduce, one RMW per row     */
+#define PB200_BWD_EXACT 3  /* same sort; every touched row written exactly once, no atomics
+                            * (deterministic; section 3b)                                */
+
+/* table element type (fbgemm SparseType weights_precision,
+ * split_table_batched_embeddings_ops.py:291) */
+#define PB200_W_F32 0
+#define PB200_W_F16 1
+
+/* optimizer fused into the backward (fbgemm OptimType, comms_utils.py:2015,
+ * split_table_batched_embeddings_ops.py:290) */
+#define PB200_OPT_SGD 1             /* exact_sgd:            w -= lr * g                          */
+#define PB200_OPT_ROWWISE_ADAGRAD 2 /* exact_row_wise_adagrad: m += mean_d(g_d^2);
+                                     *                         w -= lr / (sqrt(m) + eps) * g     */
 
 /* ---- library info -------------------------------------------------------- */
 int pb200_abi_version(void);
@@ -119,6 +132,16 @@ int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offsets /* devi
                   float *out, int64_t out_stride_t, int64_t out_stride_b,
                   int32_t algo, void *stream);
 
+/* Same, fp16 tables (weights_precision = fp16): weights_f16 is a __half arena [sum rows, dim],
+ * dim % 4 == 0, 8 B aligned.  Rows are converted to fp32 on load; accumulation and output are
+ * fp32, so the result equals pb200_tbe_fwd on the table converted to fp32, bit for bit. */
+int pb200_tbe_fwd_f16(const void *weights_f16, const int64_t *table_row_offsets,
+                      int32_t num_tables, int32_t dim,
+                      const void *indices, int64_t n_indices,
+                      const void *offsets, int64_t batch, int32_t idx_type,
+                      const float *psw, int32_t pool_mode,
+                      float *out, int64_t out_stride_t, int64_t out_stride_b, void *stream);
+
 /* Debug-mode bounds check (ATen raises on an out-of-range index; the fast path
  * does not check).  Writes the number of offending lookups to *bad_count_dev
  * (device int64, zeroed by this call).  Table-relative indices, same layout as
@@ -142,8 +165,9 @@ int pb200_check_indices(const int64_t *table_row_offsets, int32_t num_tables,
  * grad_out element (t, b, d) at grad_out[t*go_stride_t + b*go_stride_b + d].
  * MEAN mode divides by the bag length.
  *
- * PB200_BWD_SORTED needs scratch: query the size with
+ * PB200_BWD_SORTED / PB200_BWD_EXACT need scratch: query the size with
  * pb200_tbe_bwd_scratch_bytes() and pass a device buffer of that size.
+ * PB200_BWD_EXACT is pb200_tbe_bwd_fused (section 3b) with SGD, lr = -scale, fp32 rows.
  */
 int64_t pb200_tbe_bwd_scratch_bytes(int64_t n_indices, int32_t num_tables, int64_t batch,
                                     int64_t total_rows, int32_t algo);
@@ -154,6 +178,41 @@ int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32_t num_tabl
                   const float *grad_out, int64_t go_stride_t, int64_t go_stride_b,
                   float scale, int32_t algo,
                   void *scratch, int64_t scratch_bytes, void *stream);
+
+/* =========================================================================
+ * 3b. Backward with the optimizer fused in ("exact": one update per touched row)
+ * =========================================================================
+ * Replaces: the fused backward + optimizer of fbgemm's
+ *   SplitTableBatchedEmbeddingBagsCodegen(optimizer=OptimType.EXACT_ROWWISE_ADAGRAD)
+ *   as built at train/comms/pt/comms_utils.py:1995-2017 and
+ *   split_table_batched_embeddings_ops.py:279-301 (optimizer, weights_precision, lr, eps,
+ *   stochastic_rounding), driven by LookupOut.backward(grad_output)
+ *   pytorch_dist_backend.py:849-857 / ...CodegenOp.backward :318-324.
+ *
+ * g[row] = sum over ALL lookups i of the request with row(t, indices[i]) == row of
+ *          psw[i] * grad_out[(t, bag(i)), :]            (MEAN: divided by the bag length)
+ * then ONE update per touched row:
+ *   PB200_OPT_SGD             w[row] -= lr * g[row]       (lr = -1 on a zeroed fp32 buffer
+ *                                                         gives the dense gradient itself)
+ *   PB200_OPT_ROWWISE_ADAGRAD state[row] += mean_d(g[row][d]^2);
+ *                             w[row] -= lr / (sqrt(state[row]) + eps) * g[row]
+ * No atomics: results are run-to-run identical.  weights: fp32 (16 B aligned) or fp16 (8 B
+ * aligned) arena, dim % 4 == 0, dim <= 512.  state: fp32 [sum rows] (ROWWISE_ADAGRAD only).
+ * stochastic_rounding != 0 (fp16 tables only): the updated weight is rounded to fp16
+ * stochastically with a counter-based generator keyed on (sr_seed, element) — pass a new
+ * sr_seed per step; 0 = round to nearest even.
+ * scratch: pb200_tbe_bwd_fused_scratch_bytes() bytes of device memory.
+ */
+int64_t pb200_tbe_bwd_fused_scratch_bytes(int64_t n_indices, int32_t num_tables, int32_t dim);
+int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *state,
+                        const int64_t *table_row_offsets, int32_t num_tables, int32_t dim,
+                        const void *indices, int64_t n_indices,
+                        const void *offsets, int64_t batch, int32_t idx_type,
+                        const float *psw, int32_t pool_mode,
+                        const float *grad_out, int64_t go_stride_t, int64_t go_stride_b,
+                        int32_t optimizer, float lr, float eps,
+                        int32_t stochastic_rounding, uint64_t sr_seed,
+                        void *scratch, int64_t scratch_bytes, void *stream);
 
 /* =========================================================================
  * 4. Peer-memory all-to-all (single node, NVLink 5 / NVSwitch)

@@ -191,3 +191,35 @@ def calculate_lengths(offsets, n_indices):
     _load().oracle_calculate_lengths(_p(offsets, C.c_int64), C.c_int64(offsets.size),
                                      C.c_int64(n_indices), _p(out, C.c_int64))
     return out
+
+
+def fused_optimizer_step(weights, grad, optimizer="exact_sgd", lr=0.01, eps=1.0e-8, state=None,
+                         touched=None):
+    """The "exact" fused optimizers of fbgemm's SplitTableBatchedEmbeddingBagsCodegen as the reference
+    builds it (train/comms/pt/comms_utils.py:2015 optimizer=OptimType.EXACT_ROWWISE_ADAGRAD;
+    train/compute/python/workloads/pytorch/split_table_batched_embeddings_ops.py:279-301 lr / eps):
+    `grad` is the dense-equivalent gradient [rows, dim] of ONE step (tbe_bwd above), i.e. the sum over
+    all lookups of a row; every touched row gets ONE update.
+
+      exact_sgd              : w -= lr * g
+      exact_row_wise_adagrad : m[row] += mean_d(g[row, d]^2);  w[row] -= lr / (sqrt(m[row]) + eps) * g[row]
+
+    fbgemm_gpu is not in the reference tree: the formulas restate its published
+    optimizers; tests/test_oracle_golden.py pins the Adagrad arithmetic (sqrt / eps placement, state
+    accumulation over steps) against torch.optim.Adagrad on gradients that are constant along a row
+    (the reference's own create_grad = ones_like, :315-316), where rowwise == elementwise.
+    Rows outside `touched` (bool [rows]; default: rows with a non-zero gradient are irrelevant because
+    an all-zero gradient leaves both w and m unchanged) are left alone.
+    Returns (new_weights float64, new_state float64 or None)."""
+    w = np.asarray(weights, dtype=np.float64).copy()
+    g = np.asarray(grad, dtype=np.float64)
+    if touched is not None:
+        g = g * np.asarray(touched, dtype=np.float64)[:, None]
+    if optimizer in ("sgd", "exact_sgd"):
+        return w - lr * g, None
+    if optimizer in ("rowwise_adagrad", "exact_row_wise_adagrad", "exact_rowwise_adagrad"):
+        m = np.zeros(w.shape[0]) if state is None else np.asarray(state, dtype=np.float64).copy()
+        m = m + (g * g).mean(axis=1)
+        mult = lr / (np.sqrt(m) + eps)
+        return w - mult[:, None] * g, m
+    raise ValueError(f"unknown optimizer {optimizer}")

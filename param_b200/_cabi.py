@@ -17,8 +17,9 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libparam_b200.so"
 # every symbol include/param_b200.h declares; tests check that the .so exports all of them
 EXPORTED_SYMBOLS = (
     "pb200_abi_version", "pb200_error_string", "pb200_launch_count", "pb200_device_info",
-    "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_check_indices",
+    "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_tbe_fwd_f16", "pb200_check_indices",
     "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd",
+    "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused",
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
     "pb200_a2a_comm_error", "pb200_a2a_single",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_tbe_fwd_a2a",
@@ -30,7 +31,9 @@ EXPORTED_SYMBOLS = (
 POOL_SUM, POOL_MEAN = 0, 1
 IDX_I64, IDX_I32 = 0, 1
 FWD_AUTO, FWD_DIRECT, FWD_STAGED, FWD_PIPELINED = 0, 1, 2, 3
-BWD_AUTO, BWD_ATOMIC, BWD_SORTED = 0, 1, 2
+BWD_AUTO, BWD_ATOMIC, BWD_SORTED, BWD_EXACT = 0, 1, 2, 3
+W_F32, W_F16 = 0, 1
+OPT_SGD, OPT_ROWWISE_ADAGRAD = 1, 2
 A2A_SIGNAL_BYTES = 4096
 A2A_MAX_RANKS = 16
 
@@ -85,10 +88,15 @@ def load():
         i32, vp)
     sig("pb200_tbe_fwd", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64,
         i32, vp)
+    sig("pb200_tbe_fwd_f16", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64,
+        vp)
     sig("pb200_check_indices", C.c_int, vp, i32, vp, i64, vp, i64, i32, vp, vp)
     sig("pb200_tbe_bwd_scratch_bytes", i64, i64, i32, i64, i64, i32)
     sig("pb200_tbe_bwd", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64,
         f32, i32, vp, i64, vp)
+    sig("pb200_tbe_bwd_fused_scratch_bytes", i64, i64, i32, i32)
+    sig("pb200_tbe_bwd_fused", C.c_int, vp, i32, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp,
+        i64, i64, i32, f32, f32, i32, u64, vp, i64, vp)
     sig("pb200_a2a_comm_create", C.c_int, C.POINTER(vp), i32, i32, C.POINTER(vp), C.POINTER(vp), i64)
     sig("pb200_a2a_comm_destroy", C.c_int, vp)
     sig("pb200_a2a_comm_config", C.c_int, vp, i32, C.c_double)

@@ -7,8 +7,8 @@ split_table_batched_embeddings_ops.py:93-135, 191-213): same collectiveArgs fiel
 grad_output), so that `backendFuncs.emb_lookup(collectiveArgs)` (pytorch_dist_backend.py:832-857)
 and the `"compute": "emb_lookup"` trace entries run on the B200 batched op.
 
-Differences: the op is B200TBE (optimizer fused into the backward = plain SGD; the reference asks
-fbgemm for EXACT_ROWWISE_ADAGRAD — SURVEY §8f item 1, not built yet), and a missing
+Differences: the op is B200TBE with optimizer="exact_row_wise_adagrad" fused into the backward, as the
+reference asks of fbgemm (OptimType.EXACT_ROWWISE_ADAGRAD, comms_utils.py:2015); a missing
 `commsParams.direction` defaults to "forward" (the reference raises AttributeError there when driven
 from commsComputeBench).
 """
@@ -67,7 +67,8 @@ def init_emb_lookup(collectiveArgs, commsParams, backendFuncs) -> None:
     dev = backendFuncs.get_device()
     collectiveArgs.emb = [
         B200TBE([(num_embeddings, collectiveArgs.emb_dim)] * batched, device=dev,
-                lr=getattr(commsParams, "emb_lr", 0.01), seed=i)
+                optimizer=getattr(commsParams, "emb_optimizer", "exact_row_wise_adagrad"),
+                learning_rate=getattr(commsParams, "emb_lr", 0.01), seed=i)
         for i in range(collectiveArgs.num_emb_ops)
     ]
     collectiveArgs.embRequests = generate_requests(collectiveArgs.num_emb_ops, collectiveArgs.batch_size,

@@ -33,8 +33,8 @@ class B200BatchedEmbeddingBagOp:
         dev = str(self.device or "cuda")
         if not dev.startswith("cuda"):
             raise PB200Error(f"{OP_NAME} runs on CUDA devices only (got {dev})")
-        if weights_precision not in ("fp32", "float32"):
-            raise PB200Error("B200 tables are fp32")
+        if float(weight_decay) != 0.0:
+            raise PB200Error("weight decay is not implemented in the fused optimizers")
         rows_list = rows if isinstance(rows, list) else [rows] * num_tables
         dims_list = dims if isinstance(dims, list) else [dims] * num_tables
         if len(rows_list) == 1:
@@ -45,8 +45,11 @@ class B200BatchedEmbeddingBagOp:
         if mode is None:
             raise PB200Error("pooling must be 0 (sum) or 1 (mean)")
         self.weighted = bool(weighted)
-        self.op = B200TBE(list(zip(rows_list, dims_list)), lr=lr, pooling_mode=mode,
-                          device=torch.device(dev))
+        # the reference's wrapper hard-codes stochastic_rounding=True (:292); it only acts on fp16 tables
+        self.op = B200TBE(list(zip(rows_list, dims_list)), learning_rate=lr, eps=eps, pooling_mode=mode,
+                          optimizer=str(getattr(optimizer, "value", optimizer)),
+                          weights_precision=str(getattr(weights_precision, "value", weights_precision)),
+                          stochastic_rounding=True, device=torch.device(dev))
 
     def cleanup(self) -> None:
         self.op = self.fwd_out = self.grad_in = None

@@ -15,46 +15,11 @@
 //          are duplicates, so the number of L2 read-modify-writes drops ~8x and hot rows no longer
 //          serialise on one L2 slice; rows wholly inside a segment are updated exactly once
 //          (deterministic), only runs crossing a segment boundary are combined by a few reds.
-#include <stdlib.h>
-
-#include <cub/device/device_radix_sort.cuh>
-
-#include "common.cuh"
+// EXACT  : emb_bwd_exact.cu — same sort, but every touched row is written exactly once (no atomics),
+//          which is what a non-linear fused optimizer (rowwise Adagrad) and fp16 tables need.
+#include "emb_bwd_common.cuh"
 
 namespace pb200 {
-
-struct BwdParams {
-    float *dst;
-    const long long *table_row_offsets;
-    const void *indices;
-    const void *offsets;
-    const float *psw;
-    const float *grad_out;
-    long long n_indices;
-    long long batch;
-    long long n_bags;
-    long long go_stride_t;
-    long long go_stride_b;
-    float scale;
-    int num_tables;
-    int dim;
-    int mean;
-};
-
-__device__ __forceinline__ void split_bag_bwd(const BwdParams &p, long long gb, int &t,
-                                              long long &b) {
-    if (p.num_tables == 1) {
-        t = 0;
-        b = gb;
-    } else if (p.n_bags < (1ll << 31)) {
-        unsigned q = (unsigned)gb / (unsigned)p.batch;
-        t = (int)q;
-        b = (long long)((unsigned)gb - q * (unsigned)p.batch);
-    } else {
-        t = (int)(gb / p.batch);
-        b = gb - (long long)t * p.batch;
-    }
-}
 
 // ------------------------------------------------------------------------------------
 // ATOMIC
@@ -154,60 +119,13 @@ __global__ void __launch_bounds__(256) tbe_bwd_generic_kernel(const BwdParams p)
 }
 
 // ------------------------------------------------------------------------------------
-// SORTED
+// SORTED (pair builder, scratch plan and chunk pipeline: emb_bwd_common.cuh)
 // ------------------------------------------------------------------------------------
-// step 1: (key, val) pairs for bags [gb_lo, gb_hi) whose lookups are [i_lo, i_hi).
-//   key = arena row relative to the chunk's first row;
-//   val = offset of the bag's gradient row inside grad_out, in float4 units (plain sum), or the
-//         lookup position relative to i_lo (weighted / mean: weight and gradient offset come from
-//         side arrays).  The segmented reduce then needs no division to find a gradient row.
-template <typename index_t, bool SIDE>
-__global__ void __launch_bounds__(256) build_pairs_kernel(const BwdParams p, long long gb_lo,
-                                                          long long gb_hi, long long i_lo,
-                                                          long long chunk_row0, unsigned *keys,
-                                                          unsigned *vals, unsigned *goff_of,
-                                                          float *w_of) {
-    // one lane group of 8 per bag keeps the index reads coalesced for typical bag sizes
-    constexpr int G = 8;
-    const int lane_g = threadIdx.x & (G - 1);
-    const long long gb = gb_lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (gb >= gb_hi) return;
-    const index_t *off = (const index_t *)p.offsets;
-    const index_t *idx = (const index_t *)p.indices;
-    const long long begin = ld_index<index_t>(off + gb);
-    const long long end = ld_index<index_t>(off + gb + 1);
-    int t;
-    long long b;
-    split_bag_bwd(p, gb, t, b);
-    const long long base_row = p.table_row_offsets[t] - chunk_row0;
-    const unsigned goff4 = (unsigned)(((long long)t * p.go_stride_t + b * p.go_stride_b) >> 2);
-    const float inv = (p.mean && end > begin) ? 1.f / (float)(end - begin) : 1.f;
-    for (long long i = begin + lane_g; i < end; i += G) {
-        const long long o = i - i_lo;
-        keys[o] = (unsigned)(base_row + ld_index<index_t>(idx + i));
-        if (SIDE) {
-            vals[o] = (unsigned)o;
-            goff_of[o] = goff4;
-            w_of[o] = (p.psw ? p.psw[i] : 1.f) * inv;
-        } else {
-            vals[o] = goff4;
-        }
-    }
-}
-
 // step 3: segmented reduce over the sorted pairs.  One lane group per kSeg sorted entries.
 // Batches of U gradient rows are loaded unconditionally (16 B per lane, rows of past-the-end
 // entries alias gradient row 0 and are masked); a batch whose first and last key equal the running
 // key — the common case under skew, where one hot row spans thousands of entries — is added without
 // any per-entry bookkeeping.  Each (segment, row) ends in ONE red.global.add.v4.f32.
-constexpr int kSeg = 128;  // measured: 128 beats 64 by 4.5 % under Zipf, costs 1.6 % under uniform indices
-
-__device__ __forceinline__ void add2b(float &a0, float &a1, float b0, float b1) {
-    asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; "
-        "mov.b64 {%0,%1}, ra; }"
-        : "+f"(a0), "+f"(a1)
-        : "f"(b0), "f"(b1));
-}
 
 template <int G, int C, bool SIDE>
 __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long long n,
@@ -350,37 +268,6 @@ __global__ void __launch_bounds__(256, 4) segment_reduce_kernel_occ4(const BwdPa
     segment_reduce_body<G, C, SIDE>(p, n, chunk_row0, keys, vals, goff_of, w_of, seg_len);
 }
 
-static int bits_for(unsigned long long n) {
-    int b = 1;
-    while (b < 32 && (1ull << b) < n) ++b;
-    return b;
-}
-
-// Chunking: tables are processed in chunks whose lookups fit the scratch buffers.
-struct SortedPlan {
-    long long max_pairs;   // capacity of keys/vals arrays
-    size_t cub_bytes;
-    size_t total_bytes;
-};
-
-static SortedPlan plan_sorted(long long n_indices, int num_tables, bool side) {
-    SortedPlan pl{};
-    // aim for <= ~64 M pairs per chunk (0.5 GB of key/val double buffers), at least one table
-    long long per_table = num_tables > 0 ? (n_indices + num_tables - 1) / num_tables : n_indices;
-    long long cap = 64ll << 20;
-    if (cap < 2 * per_table) cap = 2 * per_table;  // slack for ragged tables; verified at run time
-    if (cap > n_indices) cap = n_indices;
-    if (cap < 1) cap = 1;
-    pl.max_pairs = cap;
-    size_t cub_bytes = 0;
-    cub::DoubleBuffer<unsigned> dk(nullptr, nullptr), dv(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int)(cap > 0x7fffffffll ? 0x7fffffff : cap), 0, 32);
-    pl.cub_bytes = (cub_bytes + 255) & ~(size_t)255;
-    size_t arr = ((size_t)cap * 4 + 255) & ~(size_t)255;
-    pl.total_bytes = pl.cub_bytes + 4 * arr + (side ? 2 * arr : 0);
-    return pl;
-}
-
 }  // namespace pb200
 
 using namespace pb200;
@@ -389,184 +276,29 @@ extern "C" int64_t pb200_tbe_bwd_scratch_bytes(int64_t n_indices, int32_t num_ta
                                                int64_t total_rows, int32_t algo) {
     (void)batch;
     (void)total_rows;
+    if (algo == PB200_BWD_EXACT)   // dim is not known here: size for the widest supported row
+        return pb200_tbe_bwd_fused_scratch_bytes(n_indices, num_tables, 512);
     if (algo != PB200_BWD_SORTED && algo != PB200_BWD_AUTO) return 0;
     if (n_indices <= 0) return 0;
-    // +table_bounds: (T+1) int64 host-mirrored lookup bounds are read back once per call
     SortedPlan pl = plan_sorted(n_indices, num_tables, true);
-    return 2 * (int64_t)pl.total_bytes + 256 + (int64_t)(num_tables + 1) * 8;   // two chunk sets
+    return (int64_t)sorted_scratch_need(pl, num_tables);
 }
 
 namespace pb200 {
 
-// gathers offsets[t*B] for t = 0..T into a small device array (then copied to the host) so the
-// host can chunk tables by lookup count without reading the whole offsets array
-template <typename index_t>
-__global__ void table_bounds_kernel(const index_t *offsets, long long batch, int num_tables,
-                                    long long *out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= num_tables) out[t] = (long long)offsets[(long long)t * batch];
-}
-
-// Scratch for one chunk in flight; two sets let chunk i+1 be built and sorted (side stream) while
-// the segmented reduce of chunk i runs (caller's stream).
-struct SortSet {
-    void *cub_tmp;
-    unsigned *k0, *k1, *v0, *v1, *goff_of;
-    float *w_of;
-};
-
-struct SortedChunk {
-    int t0, t1;
-    long long i_lo, n, row0, row1, gb_lo, gb_hi;
-    const unsigned *ks, *vs;
-};
-
 template <typename index_t>
 static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes, cudaStream_t st) {
     const bool side = (p.psw != nullptr) || p.mean;
-    const int T = p.num_tables;
-    static const int seg_len = [] {
-        const char *e = getenv("PB200_SEG");   // sorted entries per lane group
-        const int v = e ? atoi(e) : kSeg;
-        return v >= 8 ? v : kSeg;
-    }();
+    const int seg_len = seg_len_from_env();
     static const int seg_occ4 = [] {
         const char *e = getenv("PB200_SEG_OCC4");
         return e ? atoi(e) : 0;
     }();
-    static const int sort_bits = [] {
-        const char *e = getenv("PB200_SORT_BITS");   // 0 = full key (default); 16 = two radix passes
-        return e ? atoi(e) : 0;
-    }();
-    static const int overlap = [] {
-        const char *e = getenv("PB200_BWD_OVERLAP");  // 1 (default): sort of chunk i+1 under reduce of chunk i
-        return e ? atoi(e) : 1;
-    }();
-    SortedPlan pl = plan_sorted(p.n_indices, T, true);
-    const long long need = 2 * (long long)pl.total_bytes + 256 + (long long)(T + 1) * 8;
-    if (!scratch || scratch_bytes < need) return PB200_EINVAL;
-    unsigned char *base = (unsigned char *)scratch;
-    const size_t arr = ((size_t)pl.max_pairs * 4 + 255) & ~(size_t)255;
-    SortSet sets[2];
-    for (int k = 0; k < 2; ++k) {
-        unsigned char *b0 = base + (size_t)k * pl.total_bytes;
-        sets[k].cub_tmp = b0;
-        sets[k].k0 = (unsigned *)(b0 + pl.cub_bytes);
-        sets[k].k1 = (unsigned *)(b0 + pl.cub_bytes + arr);
-        sets[k].v0 = (unsigned *)(b0 + pl.cub_bytes + 2 * arr);
-        sets[k].v1 = (unsigned *)(b0 + pl.cub_bytes + 3 * arr);
-        sets[k].goff_of = (unsigned *)(b0 + pl.cub_bytes + 4 * arr);
-        sets[k].w_of = (float *)(b0 + pl.cub_bytes + 5 * arr);
-    }
-    long long *d_bounds = (long long *)(base + 2 * pl.total_bytes);
-
-    // table boundaries in lookup space and row space -> host (T+1 values each; tiny, one sync)
-    table_bounds_kernel<index_t><<<(T + 1 + 127) / 128, 128, 0, st>>>((const index_t *)p.offsets,
-                                                                      p.batch, T, d_bounds);
-    count_launch();
-    PB200_LAUNCH_CHECK();
-    static thread_local long long *h_bounds = nullptr;
-    static thread_local long long *h_rows = nullptr;
-    static thread_local int h_cap = 0;
-    if (h_cap < T + 1) {
-        if (h_bounds) cudaFreeHost(h_bounds);
-        if (h_rows) cudaFreeHost(h_rows);
-        PB200_CUDA_TRY(cudaMallocHost(&h_bounds, (size_t)(T + 1) * 8));
-        PB200_CUDA_TRY(cudaMallocHost(&h_rows, (size_t)(T + 1) * 8));
-        h_cap = T + 1;
-    }
-    PB200_CUDA_TRY(cudaMemcpyAsync(h_bounds, d_bounds, (size_t)(T + 1) * 8, cudaMemcpyDeviceToHost, st));
-    PB200_CUDA_TRY(cudaMemcpyAsync(h_rows, p.table_row_offsets, (size_t)(T + 1) * 8,
-                                   cudaMemcpyDeviceToHost, st));
-    PB200_CUDA_TRY(cudaStreamSynchronize(st));
-
+    const SortedPlan pl = plan_sorted(p.n_indices, p.num_tables, true);
     const int vec4 = p.dim >> 2;
-    // gradient row offsets travel as 32-bit float4 indices
-    {
-        const long long last = (long long)(T - 1) * p.go_stride_t + (p.batch - 1) * p.go_stride_b + p.dim;
-        if ((last >> 2) >= 0xffffffffll) return PB200_EUNSUPPORTED;
-    }
 
-    // ---- chunk plan (host) ----
-    static thread_local SortedChunk *chunks = nullptr;
-    static thread_local int chunks_cap = 0;
-    if (chunks_cap < T) {
-        free(chunks);
-        chunks = (SortedChunk *)malloc(sizeof(SortedChunk) * (size_t)T);
-        if (!chunks) return PB200_EINVAL;
-        chunks_cap = T;
-    }
-    int n_chunks = 0;
-    for (int t0 = 0; t0 < T;) {
-        int t1 = t0 + 1;
-        // grow the chunk while its lookups fit the scratch AND its rows fit 24 key bits: the radix
-        // sort then needs 3 passes instead of 4 (measured: 1/4 of the sort time at 48 tables/chunk)
-        while (t1 < T && h_bounds[t1 + 1] - h_bounds[t0] <= pl.max_pairs &&
-               h_rows[t1 + 1] - h_rows[t0] <= (1ll << 24))
-            ++t1;
-        SortedChunk c{};
-        c.t0 = t0;
-        c.t1 = t1;
-        c.i_lo = h_bounds[t0];
-        c.n = h_bounds[t1] - h_bounds[t0];
-        c.row0 = h_rows[t0];
-        c.row1 = h_rows[t1];
-        c.gb_lo = (long long)t0 * p.batch;
-        c.gb_hi = (long long)t1 * p.batch;
-        if (c.n > pl.max_pairs) return PB200_EUNSUPPORTED;  // one table larger than the scratch plan
-        if (c.row1 - c.row0 > 0xffffffffll) return PB200_EUNSUPPORTED;
-        if (c.gb_hi - c.gb_lo > 0xffffffffll || c.n > 0x7fffffffll) return PB200_EUNSUPPORTED;
-        if ((c.gb_hi - c.gb_lo) * 8 / 256 > 0x7fffffffll) return PB200_EUNSUPPORTED;
-        if (c.n > 0) chunks[n_chunks++] = c;
-        t0 = t1;
-    }
-    if (n_chunks == 0) return PB200_OK;
-
-    // ---- side stream + events (created once per host thread) ----
-    static thread_local cudaStream_t s2 = nullptr;
-    static thread_local cudaEvent_t ev_start = nullptr, ev_sorted[2] = {nullptr, nullptr},
-                                    ev_seg[2] = {nullptr, nullptr};
-    const bool use_overlap = overlap && n_chunks > 1;
-    if (use_overlap && !s2) {
-        PB200_CUDA_TRY(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-        for (int k = 0; k < 2; ++k) {
-            PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_sorted[k], cudaEventDisableTiming));
-            PB200_CUDA_TRY(cudaEventCreateWithFlags(&ev_seg[k], cudaEventDisableTiming));
-        }
-    }
-
-    // build (row, gradient offset) pairs of chunk c and sort them by row, on stream s
-    auto prepare = [&](int ci, cudaStream_t s) -> int {
-        SortedChunk &c = chunks[ci];
-        const SortSet &ss = sets[ci & 1];
-        const long long threads = (c.gb_hi - c.gb_lo) * 8;
-        const long long grid = (threads + 255) / 256;
-        if (side)
-            build_pairs_kernel<index_t, true><<<(unsigned)grid, 256, 0, s>>>(
-                p, c.gb_lo, c.gb_hi, c.i_lo, c.row0, ss.k0, ss.v0, ss.goff_of, ss.w_of);
-        else
-            build_pairs_kernel<index_t, false><<<(unsigned)grid, 256, 0, s>>>(
-                p, c.gb_lo, c.gb_hi, c.i_lo, c.row0, ss.k0, ss.v0, nullptr, nullptr);
-        count_launch();
-        PB200_LAUNCH_CHECK();
-        cub::DoubleBuffer<unsigned> dk(ss.k0, ss.k1), dv(ss.v0, ss.v1);
-        size_t tmp = pl.cub_bytes;
-        // Grouping, not ordering, is what the segmented reduce needs: PB200_SORT_BITS > 0 sorts on
-        // the low bits of the row id only (stable), one radix pass less at the price of more reds.
-        int key_bits = bits_for((unsigned long long)(c.row1 - c.row0));
-        if (sort_bits > 0 && key_bits > sort_bits) key_bits = sort_bits;
-        PB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ss.cub_tmp, tmp, dk, dv, (int)c.n, 0, key_bits, s));
-        count_launch(4);  // onesweep: histogram + scan + digit passes (library kernels)
-        c.ks = dk.Current();
-        c.vs = dv.Current();
-        return PB200_OK;
-    };
-
-    // segmented reduce of chunk c on the caller's stream
-    auto reduce = [&](int ci) -> int {
-        const SortedChunk &c = chunks[ci];
-        const SortSet &ss = sets[ci & 1];
+    // segmented reduce of one sorted chunk
+    auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
         const long long n = c.n, row0 = c.row0;
         const unsigned *ks = c.ks, *vs = c.vs;
         const long long n_seg = (n + seg_len - 1) / seg_len;
@@ -575,13 +307,13 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         const long long per_block = 8ll * (32 / G_);                                            \
         const long long g2 = (n_seg + per_block - 1) / per_block;                               \
         if (side)                                                                               \
-            segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, st>>>(                  \
+            segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, s>>>(                   \
                 p, n, row0, ks, vs, ss.goff_of, ss.w_of, seg_len);                              \
         else if (seg_occ4)                                                                      \
-            segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(            \
+            segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, s>>>(             \
                 p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
         else                                                                                    \
-            segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(                 \
+            segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, s>>>(                  \
                 p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
     } while (0)
         if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
@@ -595,36 +327,7 @@ static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes
         PB200_LAUNCH_CHECK();
         return PB200_OK;
     };
-
-    if (!use_overlap) {
-        for (int ci = 0; ci < n_chunks; ++ci) {
-            int rc = prepare(ci, st);
-            if (rc != PB200_OK) return rc;
-            rc = reduce(ci);
-            if (rc != PB200_OK) return rc;
-        }
-        return PB200_OK;
-    }
-
-    // software pipeline over chunks: prepare(i+1) on the side stream while reduce(i) runs on `st`
-    PB200_CUDA_TRY(cudaEventRecord(ev_start, st));          // inputs are ready at this point of `st`
-    PB200_CUDA_TRY(cudaStreamWaitEvent(s2, ev_start, 0));
-    int rc = prepare(0, st);
-    if (rc != PB200_OK) return rc;
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        if (ci + 1 < n_chunks) {
-            // set (ci+1)&1 was last read by reduce(ci-1): wait for it before overwriting
-            if (ci >= 1) PB200_CUDA_TRY(cudaStreamWaitEvent(s2, ev_seg[(ci + 1) & 1], 0));
-            rc = prepare(ci + 1, s2);
-            if (rc != PB200_OK) return rc;
-            PB200_CUDA_TRY(cudaEventRecord(ev_sorted[(ci + 1) & 1], s2));
-        }
-        if (ci >= 1) PB200_CUDA_TRY(cudaStreamWaitEvent(st, ev_sorted[ci & 1], 0));
-        rc = reduce(ci);
-        if (rc != PB200_OK) return rc;
-        PB200_CUDA_TRY(cudaEventRecord(ev_seg[ci & 1], st));
-    }
-    return PB200_OK;
+    return bwd_sorted_pipeline<index_t>(p, pl, scratch, scratch_bytes, st, /*full_key=*/false, reduce);
 }
 
 template <typename index_t, int G, int C>
@@ -680,7 +383,12 @@ extern "C" int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_BWD_AUTO || algo > PB200_BWD_SORTED) return PB200_EINVAL;
+    if (algo < PB200_BWD_AUTO || algo > PB200_BWD_EXACT) return PB200_EINVAL;
+    if (algo == PB200_BWD_EXACT)   // dst -= (-scale) * dW with every touched row written exactly once
+        return pb200_tbe_bwd_fused(dst, PB200_W_F32, nullptr, table_row_offsets, num_tables, dim,
+                                   indices, n_indices, offsets, batch, idx_type, psw, pool_mode,
+                                   grad_out, go_stride_t, go_stride_b, PB200_OPT_SGD, -scale, 0.f, 0,
+                                   0, scratch, scratch_bytes, stream);
     BwdParams p{};
     p.dst = dst;
     p.table_row_offsets = (const long long *)table_row_offsets;

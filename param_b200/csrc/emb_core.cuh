@@ -1,12 +1,14 @@
 // emb_core.cuh — the gather/accumulate core shared by the forward kernels (emb_fwd.cu) and the fused
 // lookup + all-to-all kernel (fused_fwd_a2a.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pb200 {
 
 struct FwdParams {
-    const float *weights;
+    const float *weights;                // fp32 arena; the fp16 kernels reinterpret it as __half
     const long long *table_row_offsets;  // device [T+1] or nullptr (single table at row 0)
     const void *indices;
     const void *offsets;
@@ -22,6 +24,7 @@ struct FwdParams {
     int has_last_offset;    // offsets has n_bags + 1 entries
     int mean;
     int stage_cap;          // STAGED: index elements per stage buffer
+    int weights_f16;        // table elements are __half (DIRECT variant only)
 };
 
 template <typename index_t>
@@ -61,13 +64,35 @@ __device__ __forceinline__ void fma2(float &a0, float &a1, float w, float b0, fl
         : "f"(w), "f"(b0), "f"(b1));
 }
 
+// A table row is read in vectors of 4 elements: 16 B of an fp32 table, 8 B of an fp16 table (converted
+// to fp32 on load; accumulation is always fp32).
+template <typename WT>
+struct RowVec;
+template <>
+struct RowVec<float> {
+    using type = float4;
+    static __device__ __forceinline__ float4 ld(const float4 *p) { return ld_row_f4(p); }
+};
+template <>
+struct RowVec<__half> {
+    using type = uint2;
+    static __device__ __forceinline__ float4 ld(const uint2 *p) {
+        uint2 raw;
+        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+        const float2 lo = __half22float2(*(const __half2 *)&raw.x);
+        const float2 hi = __half22float2(*(const __half2 *)&raw.y);
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+};
+
 // Accumulate one bag (or, for G < 32, 32/G bags side by side) given per-group [begin, end).
 // The hot loop is branch- and predicate-free: rows are consumed in batches of 8/4/2/1 whose size is
 // warp-uniform, every lane issues its loads unconditionally (lanes beyond dim/4 read column 0 and
 // drop the result at the store), and only groups shorter than the longest bag of the warp mask
 // their tail.  Per row and warp that is 1 SHFL + 1 IMAD.WIDE + 1 LDG.128 + 2 FADD2.
-template <typename index_t, int G, int C, bool WEIGHTED, int U>
+template <typename index_t, int G, int C, bool WEIGHTED, int U, typename WT = float>
 struct BagAccum {
+    using V = typename RowVec<WT>::type;
     float4 acc[C];
 
     __device__ __forceinline__ void zero() {
@@ -77,7 +102,7 @@ struct BagAccum {
 
     // N rows starting at lane j of the group; MASKED: rows at or beyond `valid` are dropped
     template <int N, bool MASKED>
-    __device__ __forceinline__ void batch(const float4 *const (&colp)[C], unsigned row_stride4,
+    __device__ __forceinline__ void batch(const V *const (&colp)[C], unsigned row_stride4,
                                           unsigned my_row, float my_w, int j, int valid) {
         float4 v[N][C];
         float wv[N];
@@ -87,7 +112,7 @@ struct BagAccum {
             if (WEIGHTED) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u, G);
             const unsigned long long roff = (unsigned long long)row * row_stride4;
 #pragma unroll
-            for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(colp[c] + roff);
+            for (int c = 0; c < C; ++c) v[u][c] = RowVec<WT>::ld(colp[c] + roff);
         }
 #pragma unroll
         for (int u = 0; u < N; ++u) {
@@ -109,7 +134,7 @@ struct BagAccum {
     }
 
     template <bool MASKED>
-    __device__ __forceinline__ void span(const float4 *const (&colp)[C], unsigned row_stride4,
+    __device__ __forceinline__ void span(const V *const (&colp)[C], unsigned row_stride4,
                                          unsigned my_row, float my_w, int j, int end, int valid) {
         for (; j + U <= end; j += U) batch<U, MASKED>(colp, row_stride4, my_row, my_w, j, valid);
         if (U > 4 && j + 4 <= end) {
@@ -131,11 +156,11 @@ struct BagAccum {
                                         int minlen, int maxlen, int lane_g, int vec4,
                                         unsigned pre_row = 0, float pre_w = 0.f) {
         const unsigned row_stride4 = (unsigned)vec4;
-        const float4 *colp[C];
+        const V *colp[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int col = c * G + lane_g;
-            colp[c] = (const float4 *)p.weights + (col < vec4 ? col : 0);
+            colp[c] = (const V *)p.weights + (col < vec4 ? col : 0);
         }
         for (int base = 0; base < maxlen; base += G) {
             // one coalesced read of up to G indices per group; out-of-bag lanes keep row 0 of the

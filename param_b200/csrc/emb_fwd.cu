@@ -27,7 +27,7 @@ namespace pb200 {
 // ------------------------------------------------------------------------------------
 // DIRECT variant
 // ------------------------------------------------------------------------------------
-template <typename index_t, int G, int C, bool WEIGHTED>
+template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float>
 __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     constexpr int BPW = 32 / G;  // bags per warp
     constexpr int U = UnrollFor<C>::value;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
     const long long base_row = (active && p.table_row_offsets) ? p.table_row_offsets[t] : 0;
 
-    BagAccum<index_t, G, C, WEIGHTED, U> acc;
+    BagAccum<index_t, G, C, WEIGHTED, U, WT> acc;
     acc.zero();
     acc.template run<false>(p, (const index_t *)p.indices + begin,
                             WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen, maxlen,
@@ -67,6 +67,13 @@ __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) 
 template <typename index_t, int G, int C, bool WEIGHTED>
 __global__ void __launch_bounds__(256, 5) tbe_fwd_direct_kernel_occ5(const FwdParams p) {
     tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
+}
+
+// fp16 tables (fbgemm weights_precision = fp16, split_table_batched_embeddings_ops.py:291): the same
+// body, rows read as 8 B vectors of 4 halves, fp32 accumulation and fp32 output.
+template <typename index_t, int G, int C, bool WEIGHTED>
+__global__ void __launch_bounds__(256) tbe_fwd_direct_f16_kernel(const FwdParams p) {
+    tbe_fwd_direct_body<index_t, G, C, WEIGHTED, __half>(p);
 }
 
 // ------------------------------------------------------------------------------------
@@ -404,7 +411,11 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
             const char *e = getenv("PB200_FWD_OCC5");
             return e ? atoi(e) : 0;
         }();
-        if (weighted)
+        if (p.weights_f16 && weighted)
+            tbe_fwd_direct_f16_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
+        else if (p.weights_f16)
+            tbe_fwd_direct_f16_kernel<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
+        else if (weighted)
             tbe_fwd_direct_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (occ5)
             tbe_fwd_direct_kernel_occ5<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
@@ -420,9 +431,15 @@ template <typename index_t>
 static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t st) {
     if (p.n_bags == 0) return PB200_OK;
     const bool vec_ok = (p.dim % 4 == 0) && (p.dim <= 512) &&
-                        (((uintptr_t)p.weights & 15) == 0) && (((uintptr_t)p.out & 15) == 0) &&
+                        (((uintptr_t)p.weights & (p.weights_f16 ? 7 : 15)) == 0) &&
+                        (((uintptr_t)p.out & 15) == 0) &&
                         (p.out_stride_t % 4 == 0) && (p.out_stride_b % 4 == 0) &&
                         (num_rows < (1ll << 32));
+    if (p.weights_f16) {
+        // fp16 tables: vector path, DIRECT variant only (no scalar fallback)
+        if (!vec_ok) return PB200_EUNSUPPORTED;
+        algo = PB200_FWD_DIRECT;
+    }
     if (!vec_ok) {
         const long long grid = (p.n_bags + 7) / 8;
         if (grid > 0x7fffffffll) return PB200_EUNSUPPORTED;
@@ -494,6 +511,38 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
     // (ops.TableArena.allocate enforces it; 180 GB of HBM / 512 B rows is 3.5e8).
     if (idx_type == PB200_IDX_I64) return dispatch_fwd<long long>(p, algo, 0, st);
     if (idx_type == PB200_IDX_I32) return dispatch_fwd<int>(p, algo, 0, st);
+    return PB200_EINVAL;
+}
+
+extern "C" int pb200_tbe_fwd_f16(const void *weights_f16, const int64_t *table_row_offsets,
+                                 int32_t num_tables, int32_t dim, const void *indices,
+                                 int64_t n_indices, const void *offsets, int64_t batch,
+                                 int32_t idx_type, const float *psw, int32_t pool_mode, float *out,
+                                 int64_t out_stride_t, int64_t out_stride_b, void *stream) {
+    if (!weights_f16 || !out || !offsets || (!indices && n_indices > 0) || !table_row_offsets)
+        return PB200_EINVAL;
+    if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
+    if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
+    FwdParams p{};
+    p.weights = (const float *)weights_f16;
+    p.weights_f16 = 1;
+    p.table_row_offsets = (const long long *)table_row_offsets;
+    p.indices = indices;
+    p.offsets = offsets;
+    p.psw = psw;
+    p.out = out;
+    p.n_indices = n_indices;
+    p.batch = batch;
+    p.n_bags = (long long)num_tables * batch;
+    p.out_stride_t = out_stride_t;
+    p.out_stride_b = out_stride_b;
+    p.num_tables = num_tables;
+    p.dim = dim;
+    p.has_last_offset = 1;
+    p.mean = pool_mode == PB200_POOL_MEAN;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_type == PB200_IDX_I64) return dispatch_fwd<long long>(p, PB200_FWD_DIRECT, 0, st);
+    if (idx_type == PB200_IDX_I32) return dispatch_fwd<int>(p, PB200_FWD_DIRECT, 0, st);
     return PB200_EINVAL;
 }
 

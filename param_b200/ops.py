@@ -13,12 +13,19 @@ from typing import Optional, Sequence
 import torch
 
 from . import _cabi
-from ._cabi import (BWD_ATOMIC, BWD_AUTO, BWD_SORTED, FWD_AUTO, FWD_DIRECT, FWD_STAGED,  # noqa: F401
-                    IDX_I32, IDX_I64, POOL_MEAN, POOL_SUM, PB200Error)
+from ._cabi import (BWD_ATOMIC, BWD_AUTO, BWD_EXACT, BWD_SORTED, FWD_AUTO, FWD_DIRECT,  # noqa: F401
+                    FWD_STAGED, IDX_I32, IDX_I64, OPT_ROWWISE_ADAGRAD, OPT_SGD, POOL_MEAN, POOL_SUM,
+                    W_F16, W_F32, PB200Error)
 
 _MODE = {"sum": POOL_SUM, "mean": POOL_MEAN}
 _FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED, "pipelined": _cabi.FWD_PIPELINED}
-_BWD_ALGO = {"auto": BWD_AUTO, "atomic": BWD_ATOMIC, "sorted": BWD_SORTED}
+_BWD_ALGO = {"auto": BWD_AUTO, "atomic": BWD_ATOMIC, "sorted": BWD_SORTED, "exact": BWD_EXACT}
+# fbgemm OptimType values as they appear in the reference's op configs
+# (split_table_batched_embeddings_ops.py:290 `OptimType(optimizer)`)
+_OPTIMIZER = {"sgd": OPT_SGD, "exact_sgd": OPT_SGD,
+              "rowwise_adagrad": OPT_ROWWISE_ADAGRAD, "exact_row_wise_adagrad": OPT_ROWWISE_ADAGRAD,
+              "exact_rowwise_adagrad": OPT_ROWWISE_ADAGRAD}
+_W_TYPE = {torch.float32: W_F32, torch.float16: W_F16}
 
 
 def _stream_ptr(t: torch.Tensor) -> int:
@@ -91,11 +98,11 @@ def embedding_bag_forward(weight: torch.Tensor, indices: torch.Tensor, offsets: 
 # --------------------------------------------------------------------------------------
 @dataclass
 class TableArena:
-    """T embedding tables in one fp32 arena [sum(rows), dim]; table t = rows
-    [row_offsets[t], row_offsets[t+1]).  Mirrors the storage of fbgemm's
+    """T embedding tables in one arena [sum(rows), dim] (fp32, or fp16 for weights_precision=fp16);
+    table t = rows [row_offsets[t], row_offsets[t+1]).  Mirrors the storage of fbgemm's
     SplitTableBatchedEmbeddingBagsCodegen (weights_offsets) that
     train/comms/pt/comms_utils.py:1995-2017 constructs, with a uniform dim."""
-    weights: torch.Tensor            # fp32 [total_rows, dim], CUDA
+    weights: torch.Tensor            # fp32 / fp16 [total_rows, dim], CUDA
     row_offsets: torch.Tensor        # int64 [T+1], CUDA
     rows: Sequence[int]              # host copy of per-table row counts
     dim: int
@@ -113,11 +120,13 @@ class TableArena:
         return self.weights[lo:lo + self.rows[t]]
 
     @staticmethod
-    def allocate(rows: Sequence[int], dim: int, device) -> "TableArena":
+    def allocate(rows: Sequence[int], dim: int, device, dtype=torch.float32) -> "TableArena":
         total = int(sum(rows))
-        if total >= 2 ** 32:
-            raise PB200Error("arena row count must stay below 2^32")
-        w = torch.empty((total, dim), dtype=torch.float32, device=device)
+        if total >= 2 ** 32 - 1:
+            raise PB200Error("arena row count must stay below 2^32 - 1")
+        if dtype not in _W_TYPE:
+            raise PB200Error("tables are fp32 or fp16")
+        w = torch.empty((total, dim), dtype=dtype, device=device)
         ro = torch.tensor([0] + list(torch.tensor(list(rows), dtype=torch.int64).cumsum(0).tolist()),
                           dtype=torch.int64, device=device)
         return TableArena(w, ro, list(int(r) for r in rows), int(dim))
@@ -152,6 +161,17 @@ def tbe_forward(arena: TableArena, indices: torch.Tensor, offsets: torch.Tensor,
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
     if batch == 0:
         return out
+    if arena.weights.dtype == torch.float16:
+        if algo not in ("auto", "direct"):
+            raise PB200Error("fp16 tables run on the DIRECT forward variant only")
+        rc = _cabi.load().pb200_tbe_fwd_f16(
+            arena.weights.data_ptr(), arena.row_offsets.data_ptr(), T, D, _ptr(indices),
+            indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode], out.data_ptr(),
+            st_t, st_b, _stream_ptr(arena.weights))
+        _cabi.check(rc, "pb200_tbe_fwd_f16")
+        return out
+    if arena.weights.dtype != torch.float32:
+        raise PB200Error("tables are fp32 or fp16")
     rc = _cabi.load().pb200_tbe_fwd(
         arena.weights.data_ptr(), arena.row_offsets.data_ptr(), T, D, _ptr(indices),
         indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode], out.data_ptr(),
@@ -196,11 +216,16 @@ def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, 
         st_t, st_b = batch * D, D
     else:
         raise PB200Error("layout must be 'BTD' or 'TBD'")
+    if dst.dtype != torch.float32:
+        raise PB200Error("tbe_backward scatters into fp32 rows; fp16 tables use tbe_backward_fused")
     lib = _cabi.load()
     a = _BWD_ALGO[algo]
     scratch_ptr, scratch_bytes = None, 0
     if a in (BWD_SORTED, BWD_AUTO):
         scratch_bytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, dst.shape[0], BWD_SORTED))
+        scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
+    elif a == BWD_EXACT:
+        scratch_bytes = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, D))
         scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
     psw = None
     if per_sample_weights is not None:
@@ -210,6 +235,58 @@ def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, 
                            grad_out.data_ptr(), st_t, st_b, float(scale), a, scratch_ptr,
                            scratch_bytes, _stream_ptr(dst))
     _cabi.check(rc, "pb200_tbe_bwd")
+
+
+def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, dim: int,
+                       indices: torch.Tensor, offsets: torch.Tensor, batch: int,
+                       grad_out: torch.Tensor, optimizer: str = "exact_sgd", lr: float = 0.01,
+                       eps: float = 1.0e-8, state: Optional[torch.Tensor] = None,
+                       layout: str = "BTD", mode: str = "sum",
+                       per_sample_weights: Optional[torch.Tensor] = None,
+                       stochastic_rounding: bool = False, sr_seed: int = 0) -> None:
+    """Backward with the optimizer fused in, one deterministic update per touched row (C ABI §3b):
+    exact_sgd `w -= lr*g` or exact_row_wise_adagrad `m += mean(g^2); w -= lr/(sqrt(m)+eps)*g`,
+    fp32 or fp16 tables.  Stands in for the fused backward of fbgemm's TBE op that the reference
+    builds at comms_utils.py:1995-2017 / split_table_batched_embeddings_ops.py:279-301."""
+    _need_cuda(weights, row_offsets, indices, offsets, grad_out, per_sample_weights, state)
+    if weights.dtype not in _W_TYPE or weights.dim() != 2 or not weights.is_contiguous():
+        raise PB200Error("weights must be a contiguous fp32 or fp16 [rows, dim] tensor")
+    if optimizer not in _OPTIMIZER:
+        raise PB200Error(f"optimizer must be one of {sorted(_OPTIMIZER)}")
+    opt = _OPTIMIZER[optimizer]
+    if opt == OPT_ROWWISE_ADAGRAD:
+        if state is None or state.dtype != torch.float32 or state.numel() != weights.shape[0] \
+                or not state.is_contiguous():
+            raise PB200Error("rowwise Adagrad needs a contiguous fp32 state with one element per arena row")
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    T, D = num_tables, dim
+    if offsets.numel() != T * batch + 1:
+        raise PB200Error("offsets must have T*batch+1 entries")
+    grad_out = grad_out.contiguous()
+    if grad_out.dtype != torch.float32 or grad_out.numel() != T * batch * D:
+        raise PB200Error("grad_out must be fp32 with T*batch*dim elements")
+    if layout == "BTD":
+        st_t, st_b = D, T * D
+    elif layout == "TBD":
+        st_t, st_b = batch * D, D
+    else:
+        raise PB200Error("layout must be 'BTD' or 'TBD'")
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+    lib = _cabi.load()
+    sb = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, D))
+    scratch = _scratch(weights.device, sb)
+    rc = lib.pb200_tbe_bwd_fused(weights.data_ptr(), _W_TYPE[weights.dtype], _ptr(state),
+                                 row_offsets.data_ptr(), T, D, _ptr(indices), indices.numel(),
+                                 _ptr(offsets), batch, it, _ptr(psw), _MODE[mode],
+                                 grad_out.data_ptr(), st_t, st_b, opt, float(lr), float(eps),
+                                 1 if stochastic_rounding else 0,
+                                 C.c_uint64(int(sr_seed) & (2 ** 64 - 1)), scratch.data_ptr(), sb,
+                                 _stream_ptr(weights))
+    _cabi.check(rc, "pb200_tbe_bwd_fused")
 
 
 def check_indices(row_offsets: torch.Tensor, num_tables: int, indices: torch.Tensor,

@@ -1,0 +1,92 @@
+"""CPU model of the run decomposition used by the EXACT backward (param_b200/csrc/emb_bwd_exact.cu):
+E1 sums runs of equal sorted keys per segment and classifies each run as final / head partial /
+tail partial; E2 stitches the runs that cross segment boundaries.  The model follows the kernels'
+rules line by line and must update every distinct key exactly once with the full sum — the property
+a non-linear fused optimizer (rowwise Adagrad) depends on.  CPU only, no oracle involved."""
+import numpy as np
+import pytest
+
+
+def _model(keys, vals, seg_len):
+    n = len(keys)
+    n_seg = (n + seg_len - 1) // seg_len
+    updates = {}                       # key -> list of sums applied (must end up with exactly one)
+    head = [None] * n_seg
+    tail = [None] * n_seg
+
+    def apply(k, s):
+        updates.setdefault(int(k), []).append(s)
+
+    # E1
+    for seg in range(n_seg):
+        s0, s1 = seg * seg_len, min((seg + 1) * seg_len, n)
+        head_cont = s0 > 0 and keys[s0 - 1] == keys[s0]
+        tail_cont = s1 < n and keys[s1] == keys[s1 - 1]
+        first_run, cur, acc = True, None, 0.0
+
+        def flush(last):
+            nonlocal first_run, acc
+            if cur is None:
+                return
+            if first_run and head_cont:
+                head[seg] = acc
+            elif last and tail_cont:
+                tail[seg] = acc
+            else:
+                apply(cur, acc)
+            first_run, acc = False, 0.0
+
+        for i in range(s0, s1):
+            if keys[i] != cur:
+                flush(False)
+                cur = keys[i]
+            acc += vals[i]
+        flush(True)
+    # E2
+    for seg in range(n_seg):
+        s0, s1 = seg * seg_len, min((seg + 1) * seg_len, n)
+        if s1 >= n:
+            continue
+        kl = keys[s1 - 1]
+        if keys[s1] != kl:
+            continue
+        if keys[s0] == kl and s0 > 0 and keys[s0 - 1] == kl:
+            continue
+        acc = tail[seg]
+        assert acc is not None, "E2 expects a tail partial that E1 did not write"
+        j = seg + 1
+        while j * seg_len < n and keys[j * seg_len] == kl:
+            assert head[j] is not None, "E2 expects a head partial that E1 did not write"
+            acc += head[j]
+            head[j] = "used"
+            j += 1
+        tail[seg] = "used"
+        apply(kl, acc)
+    assert all(h in (None, "used") for h in head), "a head partial was written but never consumed"
+    assert all(t in (None, "used") for t in tail), "a tail partial was written but never consumed"
+    return updates
+
+
+@pytest.mark.parametrize("seg_len", [1, 2, 3, 8, 128])
+@pytest.mark.parametrize("n_keys,n", [(1, 1), (1, 700), (3, 50), (5, 1000), (400, 1000), (1000, 300), (7, 128), (2, 256)])
+def test_every_key_is_updated_once_with_its_full_sum(seg_len, n_keys, n):
+    rng = np.random.default_rng(seg_len * 1000 + n_keys + n)
+    # skewed draws so that some keys span many segments and others sit inside one
+    keys = np.sort(np.minimum((rng.pareto(1.2, size=n)).astype(np.int64), n_keys - 1))
+    vals = rng.integers(1, 100, size=n).astype(np.float64)     # integers: sums are exact in any order
+    updates = _model(keys, vals, seg_len)
+    want = {int(k): float(vals[keys == k].sum()) for k in np.unique(keys)}
+    assert set(updates) == set(want)
+    for k, sums in updates.items():
+        assert len(sums) == 1, f"key {k} updated {len(sums)} times"
+        assert sums[0] == want[k]
+
+
+def test_runs_aligned_to_segment_boundaries():
+    # runs that start and end exactly on segment boundaries, incl. a run of exactly k segments
+    seg = 4
+    keys = np.array([0] * 4 + [1] * 8 + [2] * 4 + [3] * 2 + [4] * 2 + [5] * 12 + [6])
+    vals = np.arange(1, len(keys) + 1, dtype=np.float64)
+    updates = _model(keys, vals, seg)
+    for k in np.unique(keys):
+        assert updates[int(k)] == [float(vals[keys == k].sum())]

@@ -342,7 +342,7 @@ def test_emb_lookup_compute_function(cuda_device, oracle):
     be = _Be()
     params = types.SimpleNamespace(direction="backward", emb_dim=64, num_embs=500, batch_size=32,
                                    num_emb_tables_per_device=4, num_emb_tables_batched=2, bag_size=5,
-                                   device="cuda", emb_lr=0.5)
+                                   device="cuda", emb_lr=0.5, emb_optimizer="exact_sgd")
     ca = types.SimpleNamespace(reuseTensors=True)    # retain_graph: the reference loops one backward per request
     init_emb_lookup(ca, params, be)
     assert ca.num_emb_ops == 2 and len(ca.emb) == 2 and len(ca.embRequests) == 2

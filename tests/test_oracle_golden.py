@@ -109,3 +109,44 @@ def test_pooled_exchange_matches_reference_autograd_functions(oracle, golden_dir
     gins = oracle.pooled_a2a_bwd([d[f"r{r}_pool_gradout"] for r in range(W)], bs, ts, E)
     for r in range(W):
         assert np.array_equal(gins[r], d[f"r{r}_pool_gradin"]), r
+
+
+def test_rowwise_adagrad_restatement_matches_torch_adagrad_on_row_constant_gradients(oracle):
+    """fbgemm_gpu (the reference's EXACT_ROWWISE_ADAGRAD, comms_utils.py:2015) is absent, so the
+    oracle's restatement is pinned where it must coincide with an optimizer that IS here: with the
+    reference's own gradient (create_grad = ones_like, split_table_batched_embeddings_ops.py:315-316)
+    every row gradient is constant along the row, mean_d(g^2) == g_d^2, and rowwise Adagrad equals
+    torch.optim.Adagrad element for element — over several steps (state accumulation)."""
+    import torch
+    rng = np.random.default_rng(5)
+    rows, dim, B, L, lr, eps = 60, 16, 40, 6, 0.05, 1e-8
+    w0 = rng.standard_normal((rows, dim)).astype(np.float32)
+    tw = torch.nn.Parameter(torch.from_numpy(w0.copy()).double())
+    opt = torch.optim.Adagrad([tw], lr=lr, eps=eps, initial_accumulator_value=0.0)
+    w, m = w0.astype(np.float64), None
+    tro = np.array([0, rows], np.int64)
+    for step in range(3):
+        idx = rng.integers(0, rows, size=B * L).astype(np.int64)
+        off = np.arange(B + 1, dtype=np.int64) * L
+        g = oracle.tbe_bwd(rows, tro, dim, idx, off, B, np.ones((B, dim), np.float32), dtype=np.float64)
+        w, m = oracle.fused_optimizer_step(w, g, "exact_row_wise_adagrad", lr=lr, eps=eps, state=m)
+        opt.zero_grad()
+        tw.grad = torch.from_numpy(g.copy())
+        opt.step()
+        np.testing.assert_allclose(w, tw.detach().numpy(), rtol=1e-12, atol=1e-12)
+    # and with dim == 1 rowwise == elementwise for ANY gradient
+    w1 = rng.standard_normal((rows, 1))
+    g1 = rng.standard_normal((rows, 1))
+    tw1 = torch.nn.Parameter(torch.from_numpy(w1.copy()))
+    opt1 = torch.optim.Adagrad([tw1], lr=lr, eps=eps)
+    tw1.grad = torch.from_numpy(g1.copy())
+    opt1.step()
+    got, _ = oracle.fused_optimizer_step(w1, g1, "exact_row_wise_adagrad", lr=lr, eps=eps)
+    np.testing.assert_allclose(got, tw1.detach().numpy(), rtol=1e-12, atol=1e-12)
+    # exact_sgd == torch.optim.SGD
+    tw2 = torch.nn.Parameter(torch.from_numpy(w1.copy()))
+    opt2 = torch.optim.SGD([tw2], lr=lr)
+    tw2.grad = torch.from_numpy(g1.copy())
+    opt2.step()
+    got2, _ = oracle.fused_optimizer_step(w1, g1, "exact_sgd", lr=lr)
+    np.testing.assert_allclose(got2, tw2.detach().numpy(), rtol=1e-12, atol=1e-12)
