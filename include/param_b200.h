@@ -317,6 +317,30 @@ int pb200_regroup_sparse(const int64_t *lengths_in, const int64_t *indices_in, i
                          int64_t *lengths_out, int64_t *offsets_out, int64_t *indices_out,
                          void *scratch, int64_t scratch_bytes, void *stream);
 
+/* SparseDataDist as ONE asynchronous call, no host round trip.
+ * Replaces: SparseDataDist.forward  train/comms/pt/dlrm.py:744-855 (lengths all_to_all, .item() /
+ *   .numpy() syncs for the index counts :801-818, indices all_to_all, splitPerTable).
+ *
+ * lengths : int64 [T_global * b]  this rank's LOCAL batch, all global tables (table-major)
+ * indices : int64 [n_indices_local] in the same order (n_indices_local = host-known tensor size)
+ * Steps on `stream`: (1) lengths all-to-all into the window at lengths_window_off
+ *   ([W][T_local][b]); (2) per-destination index counts, kept in device memory; (3) indices
+ *   all-to-all whose block sizes the push kernel reads from device memory — source r writes into
+ *   the fixed slot [indices_window_off + r*slot_elems*8, +slot_elems*8) of the receiver's window
+ *   (slot_elems >= the most indices one rank can send to another: T_local_max * b * max bag);
+ *   (4) regroup as pb200_regroup_sparse.  A block larger than its slot is truncated and
+ *   pb200_a2a_comm_error() reports 2.
+ * Outputs (device): lengths_out int64[T_local*W*b], offsets_out int64[T_local*W*b + 1],
+ *   indices_out int64 capacity W*slot_elems (valid prefix: offsets_out[last]).
+ * scratch: pb200_regroup_scratch_bytes(world, T_local, b) bytes.  Graph-capturable.
+ */
+int pb200_sparse_data_dist(pb200_a2a_comm *comm, const int64_t *lengths, const int64_t *indices,
+                           int64_t n_indices_local, const int64_t *tables_split /* host [W] */,
+                           int64_t local_batch, int64_t lengths_window_off,
+                           int64_t indices_window_off, int64_t slot_elems,
+                           int64_t *lengths_out, int64_t *offsets_out, int64_t *indices_out,
+                           void *scratch, int64_t scratch_bytes, void *stream);
+
 /* =========================================================================
  * 7. Host-buffer entry (end-to-end path: H2D + kernels + D2H inside the call)
  * =========================================================================

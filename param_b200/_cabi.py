@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
     "pb200_a2a_comm_error", "pb200_a2a_single",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_tbe_fwd_a2a",
-    "pb200_regroup_scratch_bytes", "pb200_regroup_sparse",
+    "pb200_regroup_scratch_bytes", "pb200_regroup_sparse", "pb200_sparse_data_dist",
     "pb200_host_ctx_create", "pb200_host_ctx_destroy", "pb200_tbe_fwd_host", "pb200_tbe_step_host",
     "pb200_fill_uniform", "pb200_fill_zipf_indices",
 )
@@ -107,6 +107,8 @@ def load():
     sig("pb200_tbe_fwd_a2a", C.c_int, vp, vp, vp, i32, i32, vp, i64, vp, i32, i32, p_i64, p_i64, i64, vp)
     sig("pb200_regroup_scratch_bytes", i64, i32, i32, i64)
     sig("pb200_regroup_sparse", C.c_int, vp, vp, i64, i32, i32, i64, vp, vp, vp, vp, i64, vp)
+    sig("pb200_sparse_data_dist", C.c_int, vp, vp, vp, i64, p_i64, i64, i64, i64, i64, vp, vp, vp, vp, i64,
+        vp)
     sig("pb200_host_ctx_create", C.c_int, C.POINTER(vp), i64, i64, i32)
     sig("pb200_host_ctx_destroy", C.c_int, vp)
     sig("pb200_tbe_fwd_host", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32)

@@ -5,9 +5,9 @@ Table-parallel embeddings + batch-parallel dense part, joined by an all-to-all (
   reference step (dlrm.py:1200-1323)                     here
   ------------------------------------------------------ ------------------------------------------
   SparseFeatures/calculateLengths (:226-277)             SparseBatch (lengths kept on the device)
-  SparseDataDist: lengths a2a, .item() sync, indices     sparse_data_dist(): peer-push a2a of lengths,
-    a2a, python splitPerTable (:744-855, :430-504)         ONE [W]-count D2H, peer-push a2a of indices,
-                                                            pb200_regroup_sparse (device)
+  SparseDataDist: lengths a2a, .item() sync, indices     sparse_data_dist(): pb200_sparse_data_dist — lengths
+    a2a, python splitPerTable (:744-855, :430-504)         push, index counts kept on the device, index push
+                                                            into fixed slots, device regroup; no host sync
   apply_emb: T_l nn.EmbeddingBag launches + stack (:363) one batched TBE launch writing [N, T_l*E]
   All2Allv_Req/Wait + 2 torch.cat (:86-218, :1253)       pb200_a2a_pooled_fwd: pooled rows pushed straight
                                                             into the peers' final [lN, T_g*E] tensors
@@ -169,14 +169,31 @@ class DLRMParallelEmbedding:
         self._pooled_local = torch.empty((self.N, self.T_local * self.E), dtype=torch.float32, device=device)
         self._saved = None
         self.fused = True
+        # device-side redistribution: every source gets a fixed slot of the index window
+        self.slot_elems = self.cap_indices // self.world
+        n_len = self.world * self.T_local * self.b
+        self._dist_out = (torch.empty(n_len, dtype=torch.int64, device=device),
+                          torch.empty(n_len + 1, dtype=torch.int64, device=device),
+                          torch.empty(self.cap_indices, dtype=torch.int64, device=device))
+        self.device_side_dist = True
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------
-    def sparse_data_dist(self, batch: SparseBatch):
+    def sparse_data_dist(self, batch: SparseBatch, device_side: Optional[bool] = None):
         """batch-parallel -> table-parallel redistribution of (lengths, indices); returns the TBE
-        request (offsets int64[T_l*N+1], indices) for this rank's tables over the GLOBAL batch."""
+        request (offsets int64[T_l*N+1], indices) for this rank's tables over the GLOBAL batch.
+        device_side=True (default): one asynchronous call, index counts never leave the device
+        (the returned indices tensor then has the window's capacity; offsets[-1] entries are valid).
+        device_side=False: the two-collective form with ONE [2, W]-count D2H in between."""
         W, b, win = self.world, self.b, self.window
         if batch.count != self.T_global or batch.batch_size != b:
             raise PB200Error("SparseBatch does not match the configured tables / local batch")
+        if self.device_side_dist if device_side is None else device_side:
+            if batch.indices.numel() > self.T_global * b * (self.cap_indices // self.cap_lengths):
+                raise PB200Error("more indices than the window was sized for (raise max_bag)")
+            _, offsets, indices = win.sparse_data_dist(batch.lengths, batch.indices, self.tables_split, b,
+                                                       self.off_lengths, self.off_indices, self.slot_elems,
+                                                       out=self._dist_out)
+            return offsets, indices
         in_splits, out_splits = lengths_exchange_splits(self.tables_split, self.rank, b)
         lengths_out = win.all_to_all_single(None, batch.lengths, out_splits, in_splits,
                                             out_window_off=self.off_lengths)

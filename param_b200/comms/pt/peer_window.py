@@ -292,6 +292,41 @@ class PeerWindow:
         N, T_l = int(sum(batch_split)), int(tables_split[self.rank])
         return self.view(out_window_off, N * T_l * E, torch.float32).view(N, T_l * E)
 
+    def sparse_data_dist(self, lengths: torch.Tensor, indices: torch.Tensor, tables_split: Sequence[int],
+                         local_batch: int, lengths_window_off: int, indices_window_off: int,
+                         slot_elems: int, out=None, stream=None):
+        """SparseDataDist (dlrm.py:744-855) as one asynchronous call with no host round trip
+        (pb200_sparse_data_dist).  lengths int64 [T_global*b], indices int64 in the same order.
+        Returns (lengths_out [T_l, W*b], offsets_out [T_l*W*b + 1], indices_out [W*slot_elems], of
+        which the first offsets_out[-1] entries are valid).  `out`: optional preallocated triple."""
+        if lengths.dtype != torch.int64 or indices.dtype != torch.int64 or not lengths.is_cuda:
+            raise PB200Error("sparse_data_dist takes int64 CUDA lengths and indices")
+        lengths, indices = lengths.contiguous().view(-1), indices.contiguous().view(-1)
+        W, b, T_l = self.world, int(local_batch), int(tables_split[self.rank])
+        if len(tables_split) != W or lengths.numel() != int(sum(tables_split)) * b:
+            raise PB200Error("lengths must have T_global*b elements and tables_split one entry per rank")
+        n = W * T_l * b
+        if out is None:
+            out = (torch.empty(n, dtype=torch.int64, device=self.device),
+                   torch.empty(n + 1, dtype=torch.int64, device=self.device),
+                   torch.empty(W * int(slot_elems), dtype=torch.int64, device=self.device))
+        lengths_out, offsets_out, indices_out = out
+        if lengths_out.numel() < n or offsets_out.numel() < n + 1 or indices_out.numel() < W * int(slot_elems):
+            raise PB200Error("preallocated outputs are too small")
+        lib = _cabi.load()
+        sb = int(lib.pb200_regroup_scratch_bytes(W, T_l, b))
+        # scratch is owned by the window (virtual ranks of a local group run concurrently on one GPU)
+        scratch = getattr(self, "_dist_scratch", None)
+        if scratch is None or scratch.numel() < sb:
+            scratch = self._dist_scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
+        rc = lib.pb200_sparse_data_dist(self._comm, lengths.data_ptr(), indices.data_ptr(), indices.numel(),
+                                        _cabi.i64_array(tables_split), b, int(lengths_window_off),
+                                        int(indices_window_off), int(slot_elems), lengths_out.data_ptr(),
+                                        offsets_out.data_ptr(), indices_out.data_ptr(), scratch.data_ptr(),
+                                        sb, self._stream(stream))
+        _cabi.check(rc, "pb200_sparse_data_dist")
+        return lengths_out[:n].view(T_l, W * b), offsets_out[:n + 1], indices_out
+
     def close(self) -> None:
         if getattr(self, "_comm", None):
             _cabi.load().pb200_a2a_comm_destroy(self._comm)

@@ -86,6 +86,22 @@ __device__ __forceinline__ void copy_linear16(int4 *__restrict__ dst, const int4
     for (; u < n; u += step) st_peer_v4(dst + u, ld_src_v4(src + u));
 }
 
+// contiguous copy of n units of 8 / 4 / 1 bytes (blocks whose addresses or sizes are not 16 B
+// aligned: int64 index blocks with uneven splits are the common case), 4 loads in flight per thread
+template <typename T>
+__device__ __forceinline__ void copy_linear_small(T *dst, const T *src, long long n) {
+    const long long step = kA2AThreads;
+    long long u = threadIdx.x;
+    for (; u + 3 * step < n; u += 4 * step) {
+        const T v0 = src[u], v1 = src[u + step], v2 = src[u + 2 * step], v3 = src[u + 3 * step];
+        dst[u] = v0;
+        dst[u + step] = v1;
+        dst[u + 2 * step] = v2;
+        dst[u + 3 * step] = v3;
+    }
+    for (; u < n; u += step) dst[u] = src[u];
+}
+
 // Copy units [u0, u1) of one destination's 2-D block; a unit is UNIT bytes, run_units = units per
 // row.  No division in the steady state: rows are walked explicitly.
 template <int UNIT>
@@ -177,10 +193,22 @@ __device__ __forceinline__ void copy_units(unsigned char *dst, long long dst_str
             }
         }
     } else {
+        if (rows == 1) {   // all_to_all_single: one contiguous range, no per-unit division
+            if (UNIT == 8)
+                copy_linear_small((long long *)dst + u0, (const long long *)src + u0, u1 - u0);
+            else if (UNIT == 4)
+                copy_linear_small((int *)dst + u0, (const int *)src + u0, u1 - u0);
+            else
+                copy_linear_small(dst + u0, src + u0, u1 - u0);
+            return;
+        }
         for (long long u = u0 + threadIdx.x; u < u1; u += kA2AThreads) {
             const long long r = u / run_units;
             const long long c = u - r * run_units;
-            if (UNIT == 4)
+            if (UNIT == 8)
+                *(long long *)(dst + r * dst_stride + c * 8) =
+                    ld_stream_i64((const long long *)(src + r * src_stride + c * 8));
+            else if (UNIT == 4)
                 *(int *)(dst + r * dst_stride + c * 4) = *(const int *)(src + r * src_stride + c * 4);
             else
                 dst[r * dst_stride + c] = src[r * src_stride + c];
@@ -223,7 +251,21 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
     //    destinations staggered by rank and by CTA so every NVSwitch port is busy.
     for (int k = 0; k < W; ++k) {
         const int j = (k == 0) ? me : (me + 1 + ((k - 1) + blockIdx.x) % (W - 1)) % W;
-        const PeerCopy pc = a.copy[j];
+        PeerCopy pc = a.copy[j];
+        if (a.dev_counts) {
+            // block sizes live in device memory (computed by an earlier kernel on this stream)
+            long long before = 0;
+            for (int k = 0; k < j; ++k) before += a.dev_counts[k];
+            long long bytes = a.dev_counts[j] * a.dev_elem_bytes;
+            if (bytes > a.dev_slot_bytes) {      // never write past the receiver's slot
+                bytes = a.dev_slot_bytes;
+                if (threadIdx.x == 0) atomicExch(a.error, 2u);
+            }
+            pc.src = a.dev_src + before * a.dev_elem_bytes;
+            pc.src_stride = pc.dst_stride = 0;
+            pc.run_bytes = bytes;
+            pc.rows = bytes > 0 ? 1 : 0;
+        }
         const long long dst_off = s_dst_off[j];
         if (pc.rows > 0 && pc.run_bytes > 0 && dst_off >= 0) {
             unsigned char *dst = a.peer_data[j] + dst_off;
@@ -233,7 +275,8 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
                                       (unsigned long long)dst;
             if (pc.rows > 1)
                 bits |= (unsigned long long)pc.src_stride | (unsigned long long)pc.dst_stride;
-            const int ul = (bits & 15ull) == 0 ? 4 : ((bits & 3ull) == 0 ? 2 : 0);
+            // (int64 payloads with uneven splits — the DLRM index exchange — are 8 B aligned)
+            const int ul = (bits & 15ull) == 0 ? 4 : ((bits & 7ull) == 0 ? 3 : ((bits & 3ull) == 0 ? 2 : 0));
             const long long run_units = pc.run_bytes >> ul;
             const long long total_units = run_units * pc.rows;
             // contiguous slice per CTA (long store runs); whole rows when the block is 2-D
@@ -250,6 +293,8 @@ __global__ void __launch_bounds__(kA2AThreads) a2a_push_kernel(const A2AArgs a) 
             if (u0 < u1) {
                 if (ul == 4)
                     copy_units<16>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
+                else if (ul == 3)
+                    copy_units<8>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
                 else if (ul == 2)
                     copy_units<4>(dst, pc.dst_stride, pc.src, pc.src_stride, run_units, pc.rows, u0, u1);
                 else
@@ -365,7 +410,7 @@ extern "C" int pb200_a2a_comm_destroy(pb200_a2a_comm *comm) {
     return PB200_OK;
 }
 
-static int a2a_launch(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st) {
+int pb200::a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st) {
     for (int r = 0; r < c->world; ++r) {
         a.peer_data[r] = c->peer_data[r];
         a.peer_pad[r] = c->peer_pad[r];
@@ -416,7 +461,7 @@ extern "C" int pb200_a2a_single(pb200_a2a_comm *c, const void *in, int64_t total
     if (in_off != total_in_bytes && in_split_bytes) return PB200_EINVAL;
     if (out_off > c->window_bytes) return PB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = a2a_launch(c, a, max_peer, st);
+    int rc = a2a_launch_args(c, a, max_peer, st);
     if (rc != PB200_OK) return rc;
     if (out && total_out > 0)
         PB200_CUDA_TRY(cudaMemcpyAsync(out, c->peer_data[c->rank] + out_window_off, (size_t)total_out,
@@ -472,7 +517,7 @@ extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t 
                 const long long bytes = E * 4 * a.copy[j].rows;
                 if (bytes > max_peer) max_peer = bytes;
             }
-            int rc = a2a_launch(c, a, max_peer, st);
+            int rc = a2a_launch_args(c, a, max_peer, st);
             if (rc != PB200_OK) return rc;
         }
         return PB200_OK;
@@ -490,7 +535,7 @@ extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t 
         if (bytes > max_peer) max_peer = bytes;
     }
     if (out_window_off + batch_split[me] * T_global * E * 4 > c->window_bytes) return PB200_EINVAL;
-    return a2a_launch(c, a, max_peer, (cudaStream_t)stream);
+    return a2a_launch_args(c, a, max_peer, (cudaStream_t)stream);
 }
 
 extern "C" int pb200_a2a_pooled_bwd(pb200_a2a_comm *c, const float *grad, int32_t emb_dim,
@@ -525,5 +570,5 @@ extern "C" int pb200_a2a_pooled_bwd(pb200_a2a_comm *c, const float *grad, int32_
         if (bytes > max_peer) max_peer = bytes;
     }
     if (out_window_off + N * T_local * E * 4 > c->window_bytes) return PB200_EINVAL;
-    return a2a_launch(c, a, max_peer, (cudaStream_t)stream);
+    return a2a_launch_args(c, a, max_peer, (cudaStream_t)stream);
 }

@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 
+struct pb200_a2a_comm;
+
 namespace pb200 {
 
 struct SignalPad {
@@ -32,6 +34,14 @@ struct A2AArgs {
     long long spin_cycles;                          // give up a flag wait after this many clocks
     int rank;
     int world;
+    // device-resident send counts (sparse input redistribution without a host round trip): when
+    // dev_counts != nullptr the block for destination j is dev_counts[j] elements starting at
+    // dev_src + (sum_{k<j} dev_counts[k]) * dev_elem_bytes, and copy[] is ignored.  The receiver
+    // gives every source a fixed slot of dev_slot_bytes (recv_off[r] = base + r * slot).
+    const long long *dev_counts;
+    const unsigned char *dev_src;
+    long long dev_elem_bytes;
+    long long dev_slot_bytes;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -77,6 +87,12 @@ __device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, uns
     return true;
 }
 
+}  // namespace pb200
+
+namespace pb200 {
+// fills the communicator fields of `a` and launches the push kernel (a2a.cu); shared with the
+// sparse-input redistribution entry (sparse_dist.cu)
+int a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st);
 }  // namespace pb200
 
 struct pb200_a2a_comm {

@@ -90,3 +90,60 @@ def test_runs_aligned_to_segment_boundaries():
     updates = _model(keys, vals, seg)
     for k in np.unique(keys):
         assert updates[int(k)] == [float(vals[keys == k].sum())]
+
+
+# ---------------------------------------------------------------------------------------------------
+# slot layout of the device-side sparse redistribution (param_b200/csrc/sparse_dist.cu)
+# ---------------------------------------------------------------------------------------------------
+def _regroup_slots_model(lengths_in, window, W, T, b, slot):
+    """seg_sum_permute + seg_starts (slot form) + seg_copy, rule for rule"""
+    seg_sum = lengths_in.reshape(W * T, b).sum(axis=1)
+    in_start = np.zeros(W * T, np.int64)
+    in_end = np.zeros(W * T, np.int64)
+    for r in range(W):
+        acc = r * slot
+        for t in range(T):
+            in_start[r * T + t] = acc
+            acc += seg_sum[r * T + t]
+            in_end[r * T + t] = acc
+    out_start = np.zeros(W * T, np.int64)
+    acc = 0
+    for t in range(T):
+        for r in range(W):
+            out_start[r * T + t] = acc
+            acc += seg_sum[r * T + t]
+    out = np.full(W * slot, -1, np.int64)
+    for i in range(W * slot):
+        lo, hi = 0, W * T - 1
+        while lo < hi:
+            mid = (lo + hi + 1) >> 1
+            if in_start[mid] <= i:
+                lo = mid
+            else:
+                hi = mid - 1
+        if in_start[lo] <= i < in_end[lo]:
+            o = out_start[lo] + (i - in_start[lo])
+            if o < W * slot:
+                out[o] = window[i]
+    return out
+
+
+@pytest.mark.parametrize("W,T,b,max_len", [(2, 3, 4, 5), (4, 2, 3, 2), (3, 1, 7, 9), (8, 4, 2, 1)])
+def test_slot_layout_regroup_model_matches_oracle(oracle, W, T, b, max_len):
+    rng = np.random.default_rng(W * 100 + T * 10 + b)
+    lengths = rng.integers(0, max_len + 1, size=W * T * b).astype(np.int64)
+    lengths[rng.integers(0, W * T * b, size=3)] = 0
+    if W > 2:
+        lengths[T * b:2 * T * b] = 0                      # a source that sends nothing
+    slot = T * b * max_len
+    window = np.full(W * slot, -7, np.int64)              # stale content in the slot tails
+    packed = []
+    for r in range(W):
+        n = int(lengths[r * T * b:(r + 1) * T * b].sum())
+        blk = rng.integers(0, 1 << 40, size=n).astype(np.int64)
+        window[r * slot:r * slot + n] = blk
+        packed.append(blk)
+    packed = np.concatenate(packed)
+    _, want_off, want_idx = oracle.split_per_table(lengths, packed, W, T, b)
+    got = _regroup_slots_model(lengths, window, W, T, b, slot)
+    assert np.array_equal(got[:want_off[-1]], want_idx)

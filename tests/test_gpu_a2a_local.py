@@ -171,3 +171,58 @@ def test_fused_lookup_exchange_vs_oracle(cuda_device, oracle, W, T, dim):
         ys = _run_all(grp, lambda r, w_, st: w_.all_to_all_single(None, xs[r], out_window_off=2 << 20, stream=st).clone())
         for r in range(W):
             assert ys[r].view(W, 8)[:, 0].tolist() == [float(s) for s in range(W)]
+
+
+@pytest.mark.parametrize("W,T,b,max_len", [(2, 4, 16, 6), (3, 7, 9, 5), (4, 4, 32, 20), (8, 19, 8, 3)])
+def test_sparse_data_dist_device_side_vs_oracle(cuda_device, oracle, W, T, b, max_len):
+    """pb200_sparse_data_dist (lengths push -> device-resident index counts -> index push into fixed
+    slots -> regroup, no host round trip) against the oracle's c10d all_to_all_single of the lengths
+    and indices followed by splitPerTable — int64, bit-exact; run twice on the same communicator with
+    different data (epochs, stale slot tails from the first round)."""
+    from param_b200.comms.pt.dlrm import split_lengths
+    rng = np.random.default_rng(W * 17 + T)
+    ts = split_lengths(T, W)
+    T_max = max(ts)
+    slot = T_max * b * max_len
+    n_len_max = W * T_max * b
+    win_bytes = (n_len_max + W * slot) * 8 + 2048
+    grp = _group(W, win_bytes, cuda_device)
+    off_len = 0
+    off_idx = (n_len_max * 8 + 511) // 512 * 512
+    bases = np.concatenate([[0], np.cumsum(ts)])
+    for rep in range(2):
+        lens_h = [rng.integers(0, max_len + 1, size=T * b).astype(np.int64) for _ in range(W)]
+        if rep == 1:
+            lens_h[0][:] = 0                                  # a rank that sends nothing at all
+        idx_h = [((np.arange(int(l.sum())) * 7 + 100000 * r + rep) % (1 << 40)).astype(np.int64)
+                 for r, l in enumerate(lens_h)]
+        # oracle: the two all_to_all_single of SparseDataDist, then splitPerTable per rank
+        len_splits = np.array([[ts[d] * b for d in range(W)] for _ in range(W)])
+        lens_recv = oracle.all_to_all_single(lens_h, len_splits)
+        idx_splits = np.array([[int(lens_h[s][bases[d] * b:bases[d + 1] * b].sum()) for d in range(W)] for s in range(W)])
+        idx_recv = oracle.all_to_all_single(idx_h, idx_splits)
+        lens_d = [torch.from_numpy(x).to(cuda_device) for x in lens_h]
+        idx_d = [torch.from_numpy(x).to(cuda_device) for x in idx_h]
+        outs = _run_all(grp, lambda r, w, st: w.sparse_data_dist(lens_d[r], idx_d[r], ts, b, off_len, off_idx, slot,
+                                                                 stream=st))
+        for r in range(W):
+            want_len, want_off, want_idx = oracle.split_per_table(lens_recv[r], idx_recv[r], W, ts[r], b)
+            got_len, got_off, got_idx = (x.cpu().numpy() for x in outs[r])
+            assert np.array_equal(got_len, want_len), (rep, r)
+            assert np.array_equal(got_off, want_off), (rep, r)
+            assert np.array_equal(got_idx[:want_off[-1]], want_idx), (rep, r)
+
+
+def test_sparse_data_dist_slot_overflow_is_reported(cuda_device):
+    """a block larger than its slot is truncated (never written past the slot) and flagged"""
+    W, T, b = 2, 2, 4
+    grp = _group(W, 1 << 16, cuda_device)
+    lens = [torch.full((T * b,), 5, dtype=torch.int64, device=cuda_device) for _ in range(W)]
+    idx = [torch.arange(T * b * 5, dtype=torch.int64, device=cuda_device) for _ in range(W)]
+    slot = 8                                                  # needs 1 table * 4 bags * 5 = 20
+    for r, (w, st) in enumerate(zip(grp.windows, grp.streams)):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            w.sparse_data_dist(lens[r], idx[r], [1, 1], b, 0, 4096, slot, stream=st)
+    torch.cuda.synchronize()
+    assert all(w.error() == 2 for w in grp.windows)

@@ -154,8 +154,12 @@ for t in range(sl.start, sl.stop):
     tbl_len.append(np.concatenate(ll))
 want_idx = np.concatenate(tbl_idx)
 want_off = np.concatenate([[0], np.cumsum(np.concatenate(tbl_len))]).astype(np.int64)
-report("sparse_data_dist (2 peer a2a + device regroup) == global regroup",
-       np.array_equal(indices.cpu().numpy(), want_idx) and np.array_equal(offsets.cpu().numpy(), want_off))
+n_valid = int(want_off[-1])
+report("sparse_data_dist (ONE call, device-resident counts, slot layout) == global regroup",
+       np.array_equal(indices.cpu().numpy()[:n_valid], want_idx) and np.array_equal(offsets.cpu().numpy(), want_off))
+off_h, idx_h = model.sparse_data_dist(batch, device_side=False)
+report("sparse_data_dist (2 peer a2a + one count D2H + device regroup) == global regroup",
+       np.array_equal(idx_h.cpu().numpy(), want_idx) and np.array_equal(off_h.cpu().numpy(), want_off))
 T_l = ts[rank]
 tro = np.arange(T_l + 1, dtype=np.int64) * rows
 pooled_ref = oracle.tbe_fwd(w0.cpu().numpy(), tro, E, want_idx, want_off, N, layout="TBD")     # [T_l, N, E]
