@@ -46,6 +46,17 @@ for what in a.what.split(","):
             ops.tbe_forward(arena, idx, off, B, algo="staged", out=out)
         elif what == "bwd_sorted":
             ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="sorted")
+        elif what == "bwd_exact":
+            ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="exact")
+        elif what == "bwd_adagrad":
+            if "state" not in globals():
+                state = torch.zeros(arena.total_rows, device=dev)
+            ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
+                                   optimizer="exact_row_wise_adagrad", lr=1e-6, state=state)
+        elif what == "fwd_f16":
+            if "a16" not in globals():
+                a16 = ops.TableArena(arena.weights.to(torch.float16), arena.row_offsets, arena.rows, D)
+            ops.tbe_forward(a16, idx, off, B, out=out)
         elif what == "bwd_atomic":
             ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="atomic")
     torch.cuda.synchronize()

@@ -41,4 +41,19 @@ def ev(fn, n=5):
 f = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out))
 bw = ev(lambda: ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="sorted"))
 knobs = {k: v for k, v in os.environ.items() if k.startswith("PB200_")}
+if os.environ.get("PB200_VARIANT_EXTRAS", "1") != "0":
+    # fused-optimizer ("exact") backward and fp16 tables on the same request
+    lookups = T * B * L
+    ex = ev(lambda: ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="exact"))
+    state = torch.zeros(arena.total_rows, device=dev)
+    ada = ev(lambda: ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
+                                            optimizer="exact_row_wise_adagrad", lr=1e-6, state=state))
+    a16 = ops.TableArena(arena.weights.to(torch.float16), arena.row_offsets, arena.rows, D)
+    f16 = ev(lambda: ops.tbe_forward(a16, idx, off, B, out=out))
+    ada16 = ev(lambda: ops.tbe_backward_fused(a16.weights, a16.row_offsets, T, D, idx, off, B, out,
+                                              optimizer="exact_row_wise_adagrad", lr=1e-6, state=state,
+                                              stochastic_rounding=True, sr_seed=7))
+    print(f"T={T} alpha={alpha} extras: bwd_exact_sgd {ex:.3f} ms  bwd_exact_rowwise_adagrad {ada:.3f} ms  "
+          f"fwd_fp16 {f16:.3f} ms ({lookups / f16 / 1e6:.2f} G lookups/s)  "
+          f"bwd_fp16_rowwise_adagrad_sr {ada16:.3f} ms")
 print(f"T={T} alpha={alpha} knobs={knobs}  fwd {f:.3f} ms  bwd_sorted {bw:.3f} ms  (x{256 // T} -> {f * 256 / T:.1f} / {bw * 256 / T:.1f} ms at 256 tables)")
