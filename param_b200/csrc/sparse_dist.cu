@@ -296,6 +296,27 @@ extern "C" int pb200_sparse_data_dist(pb200_a2a_comm *c, const int64_t *lengths,
     unsigned char *sbase = (unsigned char *)scratch;
     long long *counts = (long long *)(sbase + pb200_regroup_scratch_bytes(W, T_l, b) - 256);
 
+    // Load every kernel of this call BEFORE the first push kernel is queued.  With CUDA's lazy module
+    // loading the first launch of a kernel may synchronise the context; if that happened behind a
+    // push kernel that is spinning on a peer which lives in the same process (virtual ranks on one
+    // GPU, tests), the peer's launches would never be issued.
+    {
+        static bool loaded = false;
+        if (!loaded) {
+            cudaFuncAttributes fa;
+            PB200_CUDA_TRY(cudaFuncGetAttributes(&fa, dest_counts_kernel));
+            PB200_CUDA_TRY(cudaFuncGetAttributes(&fa, seg_sum_permute_kernel));
+            PB200_CUDA_TRY(cudaFuncGetAttributes(&fa, seg_starts_kernel));
+            PB200_CUDA_TRY(cudaFuncGetAttributes(&fa, seg_copy_kernel));
+            PB200_CUDA_TRY(cudaFuncGetAttributes(&fa, write_total_kernel));
+            size_t tmp = scan_tmp_bytes(1);
+            PB200_CUDA_TRY(cub::DeviceScan::ExclusiveSum(sbase, tmp, (const long long *)counts,
+                                                         (long long *)counts, 1, st));   // cub's kernels
+            PB200_CUDA_TRY(cudaStreamSynchronize(st));
+            loaded = true;
+        }
+    }
+
     // 1. lengths: rank j receives the lengths of ITS tables from everyone (dlrm.py:768-785)
     long long in_split[PB200_A2A_MAX_RANKS], out_split[PB200_A2A_MAX_RANKS];
     for (int r = 0; r < W; ++r) {

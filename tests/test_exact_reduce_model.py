@@ -147,3 +147,55 @@ def test_slot_layout_regroup_model_matches_oracle(oracle, W, T, b, max_len):
     _, want_off, want_idx = oracle.split_per_table(lengths, packed, W, T, b)
     got = _regroup_slots_model(lengths, window, W, T, b, slot)
     assert np.array_equal(got[:want_off[-1]], want_idx)
+
+
+# ---------------------------------------------------------------------------------------------------
+# prefetch bookkeeping of E1 (state / old weights are loaded with the batch, not at the flush)
+# ---------------------------------------------------------------------------------------------------
+def _e1_prefetch_model(keys, G, U):
+    """One lane group walking one segment in G-blocks and U-batches like exact_reduce_kernel.  Every
+    flush must find cur_state == the prefetch of the row it is about to update."""
+    my_n = len(keys)
+    cur_key, cur_state, flushed = None, None, []
+
+    def flush():
+        nonlocal cur_key
+        if cur_key is not None:
+            assert cur_state == ("state-of", cur_key), (cur_key, cur_state)
+            flushed.append(cur_key)
+
+    for base in range(0, my_n, G):
+        valid = my_n - base
+        cnt = min(G, my_n - base)
+        for j0 in range(0, cnt, U):
+            kk = [keys[base + j0 + u] if (j0 + u < valid and j0 + u < G) else 0 for u in range(U)]
+            st = []
+            for u in range(U):
+                ok_u = (j0 + u < valid) and (j0 + u < G)
+                ok_n = (u + 1 < U) and (j0 + u + 1 < valid) and (j0 + u + 1 < G)
+                ends = ok_u and (not ok_n or kk[u + 1 if u + 1 < U else u] != kk[u])
+                st.append(("state-of", kk[u]) if ends else None)
+            all_valid = (j0 + U <= valid) and (j0 + U <= G)
+            same = kk[U - 1] == kk[0]
+            if all_valid and same and (kk[0] == cur_key or cur_key is None):
+                cur_key = kk[0]
+                cur_state = st[U - 1]
+            else:
+                for u in range(U):
+                    if j0 + u < valid and j0 + u < G:
+                        if kk[u] != cur_key:
+                            flush()
+                            cur_key = kk[u]
+                        cur_state = st[u]
+    flush()
+    return flushed
+
+
+@pytest.mark.parametrize("G,U", [(32, 8), (32, 4), (32, 2), (16, 8), (8, 8), (4, 8)])
+def test_prefetched_state_always_belongs_to_the_flushed_row(G, U):
+    rng = np.random.default_rng(G * 10 + U)
+    for n in (1, 2, 7, 8, 9, 31, 32, 33, 100, 128):
+        for n_keys in (1, 2, 5, 200):
+            keys = np.sort(rng.integers(0, n_keys, size=n)).tolist()
+            flushed = _e1_prefetch_model(keys, G, U)
+            assert flushed == sorted(set(keys))
