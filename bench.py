@@ -225,6 +225,21 @@ def run_b200(args):
     except Exception as exc:  # noqa: BLE001
         ms_bwd_other = f"failed: {exc}"
 
+    # the fused-optimizer backward (one deterministic update per touched row, C ABI §3b): exact SGD and
+    # fbgemm's default exact rowwise Adagrad (what comms_utils.py:2015 asks for)
+    ms_bwd_exact = ms_bwd_adagrad = None
+    try:
+        ms_bwd_exact = ev_time(lambda: ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
+                                                              optimizer="exact_sgd", lr=args.lr), max(2, args.steps // 2))
+        state = torch.zeros(arena.total_rows, dtype=torch.float32, device=dev)
+        ms_bwd_adagrad = ev_time(lambda: ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B,
+                                                                out, optimizer="exact_row_wise_adagrad", lr=args.lr,
+                                                                state=state), max(2, args.steps // 2))
+        del state
+    except Exception as exc:  # noqa: BLE001
+        ms_bwd_exact = ms_bwd_exact if ms_bwd_exact is not None else f"failed: {exc}"
+        ms_bwd_adagrad = f"failed: {exc}"
+
     peak, peak_src = measured_peaks()
     fwd_bytes, bwd_bytes = algorithmic_bytes(T, B, L, D)
     # `roofline` is quoted for the forward lookup kernel: ONE launch per step, the kernel north_star's
@@ -270,7 +285,10 @@ def run_b200(args):
                                 param_bw_gbs=round(lookups * D * 4 / ms_fwd / 1e6, 1)),
                     "fwd_direct_ms": round(ms_fwd_direct, 4), "fwd_staged_ms": round(ms_fwd_staged, 4), "fwd_pipelined_ms": round(ms_fwd_pipe, 4),
                     "bwd": dict(roof(bwd_bytes, ms_bwd), ms=round(ms_bwd, 4), algo=bwd_algo),
-                    f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4)},
+                    f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4),
+                    "bwd_exact_sgd_ms": ms_bwd_exact if not isinstance(ms_bwd_exact, float) else round(ms_bwd_exact, 4),
+                    "bwd_exact_rowwise_adagrad_ms": ms_bwd_adagrad if not isinstance(ms_bwd_adagrad, float)
+                    else round(ms_bwd_adagrad, 4)},
         "clocks": clk.summary(),
     }
     if rank == 0 and not args.skip_e2e:
