@@ -238,13 +238,21 @@ static int bwd_sorted_pipeline(const BwdParams &p, const SortedPlan &pl, void *s
         if (!chunks) return PB200_EINVAL;
         chunks_cap = T;
     }
+    static const long long min_pairs = [] {
+        const char *e = getenv("PB200_CHUNK_MIN_PAIRS");
+        return e ? atoll(e) : (8ll << 20);
+    }();
     int n_chunks = 0;
     for (int t0 = 0; t0 < T;) {
         int t1 = t0 + 1;
         // grow the chunk while its lookups fit the scratch AND its rows fit 24 key bits: the radix
-        // sort then needs 3 passes instead of 4 (measured: 1/4 of the sort time at 48 tables/chunk)
+        // sort then needs 3 passes instead of 4 (measured: 1/4 of the sort time at 48 tables/chunk).
+        // Tables with many rows but few lookups (10 M rows, 1.3 M lookups each) would end up one per
+        // chunk, each paying the launch latency of ~10 small kernels: below min_pairs lookups the
+        // 24-bit rule gives way (a fourth radix pass is cheaper than 7x the launches).
         while (t1 < T && h_bounds[t1 + 1] - h_bounds[t0] <= pl.max_pairs &&
-               h_rows[t1 + 1] - h_rows[t0] <= (1ll << 24))
+               h_rows[t1 + 1] - h_rows[t0] < 0xffffffffll &&
+               (h_rows[t1 + 1] - h_rows[t0] <= (1ll << 24) || h_bounds[t1] - h_bounds[t0] < min_pairs))
             ++t1;
         SortedChunk c{};
         c.t0 = t0;

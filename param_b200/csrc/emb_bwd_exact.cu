@@ -22,10 +22,10 @@
 //                            first run if it continues the previous segment's last row, and the
 //                            last run if it continues into the next segment, go to a partial-sum
 //                            buffer instead ([segment][head|tail][dim] fp32).
-//   E2 exact_boundary_kernel one lane group per segment whose tail run STARTS a multi-segment
-//                            run: tail partial + head partials of the following segments while
-//                            they begin with the same row (8 independent 16 B loads in flight —
-//                            the hottest Zipf row spans hundreds of segments), then the update.
+//   E2 exact_boundary_kernel one CTA per segment whose tail run STARTS a multi-segment run: tail
+//                            partial + head partials of the following segments while they begin
+//                            with the same row, walked by the CTA's lane groups interleaved (the
+//                            hottest Zipf row spans hundreds of segments), then the update.
 // Summation order is fixed by the sort (stable radix sort of a fixed pair order) and the segment
 // structure, so two runs on the same inputs give identical bits.
 #include <cuda_fp16.h>
@@ -362,6 +362,13 @@ __global__ void __launch_bounds__(256) exact_reduce_kernel(const BwdParams p, co
 }
 
 // ---- E2 ----------------------------------------------------------------------------------------
+// One CTA per segment; only CTAs whose segment's tail run STARTS a multi-segment run do any work.
+// The 256/G lane groups of the CTA walk the following segments interleaved (group w takes segments
+// seg+1+w, seg+1+w+NW, ...; U head partials in flight each), so the hottest Zipf row — up to one
+// lookup per bag = 512 segments at batch 65536 — is summed in ~8 dependent steps instead of 64;
+// with one 10 M-row table per chunk that chain was the critical path of the whole chunk
+// (profiles/r01e: 6.3 ms vs 3.7 ms for SORTED at 25 tables).  The group sums are combined through
+// shared memory in group order: the summation order stays fixed, results stay deterministic.
 template <typename WT, int G, int C>
 __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, const OptParams op,
                                                              long long n, long long chunk_row0,
@@ -369,14 +376,18 @@ __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, 
                                                              const float4 *__restrict__ partial,
                                                              int seg_len) {
     constexpr int BPW = 32 / G;
+    constexpr int NW = 8 * BPW;          // lane groups per CTA
     constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
+    __shared__ float4 s_part[256 * C];   // [NW][C*G]
     const int lane = threadIdx.x & 31;
     const int lane_g = lane & (G - 1);
     const int grp = lane / G;
+    const int worker = (threadIdx.x >> 5) * BPW + grp;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int vec4 = p.dim >> 2;
-    const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
+    const long long seg = blockIdx.x;
     const long long s0 = seg * seg_len;
+    // CTA-uniform exits (before the barrier)
     if (s0 >= n) return;
     const long long s1 = min(s0 + (long long)seg_len, n);
     if (s1 >= n) return;                                   // the last segment has no successor
@@ -392,15 +403,16 @@ __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, 
     for (int c = 0; c < C; ++c) {
         const int col = c * G + lane_g;
         col_ok[c] = col < vec4;
-        acc[c] = col_ok[c] ? ld_stream_f4(tail + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[c] = (worker == 0 && col_ok[c]) ? ld_stream_f4(tail + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    bool done = false;
-    for (long long j = seg + 1; !done; j += U) {
+    const long long first = seg + 1 + worker;
+    bool done = !(first * seg_len < n && keys[first * seg_len] == kl);   // most runs end in the next segment
+    for (long long j = first; !done; j += (long long)NW * U) {
         float4 v[U][C];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long jj = j + u;
+            const long long jj = j + (long long)u * NW;
             const long long pos = jj * seg_len;
             const bool in = pos < n;
             ok[u] = in && keys[in ? pos : 0] == kl;
@@ -424,6 +436,19 @@ __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, 
                     done = true;
                 }
             }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_part[worker * (C * G) + c * G + lane_g] = acc[c];
+    __syncthreads();
+    if (worker != 0) return;
+#pragma unroll 1
+    for (int w = 1; w < NW; ++w) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float4 x = s_part[w * (C * G) + c * G + lane_g];
+            add2b(acc[c].x, acc[c].y, x.x, x.y);
+            add2b(acc[c].z, acc[c].w, x.z, x.w);
         }
     }
     apply_row_update<WT, G, C>(op, (unsigned long long)chunk_row0 + kl, acc, col_ok, lane_g, vec4,
@@ -467,8 +492,8 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
             exact_reduce_kernel<WT, PB200_OPT_SGD, G_, C_, false>                                  \
                 <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
         if (n_seg > 1)                                                                             \
-            exact_boundary_kernel<WT, G_, C_><<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks,     \
-                                                                          partial, seg_len);      \
+            exact_boundary_kernel<WT, G_, C_><<<(unsigned)n_seg, 256, 0, s>>>(p, op, n, row0, ks,  \
+                                                                             partial, seg_len);   \
     } while (0)
         if (vec4 <= 4) PB200_EXACT_LAUNCH(4, 1);
         else if (vec4 <= 8) PB200_EXACT_LAUNCH(8, 1);

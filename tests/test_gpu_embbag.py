@@ -242,7 +242,7 @@ def test_large_shape_properties(cuda_device):
     got = out_d.double().sum()
     assert abs(float(got - want)) <= 1e-6 * float(row_sum[idx + base].abs().sum())
     # backward: round trip of counts — dW from an all-ones grad is the per-row hit count
-    for algo in ("atomic", "sorted"):
+    for algo in ("atomic", "sorted", "exact"):
         dst = torch.zeros_like(ar.weights)
         ops.tbe_backward(dst, ar.row_offsets, T, dim, idx, off, B, torch.ones(B, T * dim, device=cuda_device),
                          layout="BTD", algo=algo)

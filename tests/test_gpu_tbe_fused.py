@@ -140,26 +140,42 @@ def test_exact_zipf_hot_rows_span_hundreds_of_segments(cuda_device, oracle):
             assert np.array_equal(w.cpu().numpy()[untouched], arena[untouched])
 
 
-def test_exact_backward_of_ones_counts_hits_exactly(cuda_device):
-    """size-independent property at a multi-chunk size (> 2^24 rows per chunk forces several chunks):
-    lr = -1, grad = ones, zero weights -> every element of a row equals its hit count, exactly"""
+def test_multi_chunk_backward_of_ones_counts_hits_exactly(cuda_device):
+    """size-independent property at a size that needs SEVERAL chunks (tables are grouped into chunks
+    of <= 2^24 rows once a chunk holds >= 8 M lookups; chunk i+1 is built and sorted on a side stream
+    under the reduce of chunk i): grad = ones into a zeroed fp32 buffer -> every element of a row
+    equals its hit count, exactly, for the EXACT and the SORTED variant."""
     from param_b200 import ops
-    T, B, L, dim, rows = 5, 8192, 8, 32, 6_000_000
+    T, B, L, dim, rows = 4, 1 << 19, 8, 32, 9_000_000
     tro = torch.arange(T + 1, dtype=torch.int64, device=cuda_device) * rows
     g = torch.Generator(device=cuda_device)
     g.manual_seed(3)
-    # half of the lookups hit 50 hot rows, half are spread over the table
-    hot = torch.randint(0, 50, (T * B * L // 2,), generator=g, device=cuda_device)
-    cold = torch.randint(0, rows, (T * B * L - hot.numel(),), generator=g, device=cuda_device)
-    idx = torch.cat([hot, cold])[torch.randperm(T * B * L, generator=g, device=cuda_device)]
+    n = T * B * L
+    # a quarter of the lookups hit 50 hot rows per table (runs of ~20 K entries = ~160 segments),
+    # the rest are spread over the table
+    idx = torch.randint(0, rows, (n,), generator=g, device=cuda_device)
+    hot = torch.rand(n, generator=g, device=cuda_device) < 0.25
+    idx[hot] = idx[hot] % 50
     off = torch.arange(T * B + 1, dtype=torch.int64, device=cuda_device) * L
-    w = torch.zeros((T * rows, dim), device=cuda_device)
-    ops.tbe_backward_fused(w, tro, T, dim, idx, off, B, torch.ones((B, T * dim), device=cuda_device),
-                           optimizer="exact_sgd", lr=-1.0)
-    table_of = torch.arange(T * B * L, device=cuda_device) // (B * L)
+    table_of = torch.arange(n, device=cuda_device) // (B * L)
     counts = torch.bincount(idx + table_of * rows, minlength=T * rows).to(torch.float32)
-    assert torch.equal(w[:, 0], counts) and torch.equal(w[:, dim - 1], counts)
-    assert float(w.sum()) == float(T * B * L * dim)
+    ones = torch.ones((B, T * dim), device=cuda_device)
+    for algo in ("exact", "sorted"):
+        w = torch.zeros((T * rows, dim), device=cuda_device)
+        ops.tbe_backward(w, tro, T, dim, idx, off, B, ones, scale=1.0, algo=algo)
+        assert torch.equal(w[:, 0], counts) and torch.equal(w[:, dim - 1], counts), algo
+        del w
+    # rowwise Adagrad on the same request: state = mean_d(count^2) = count^2 exactly (counts < 2^10: every partial sum k*count^2 fits 24 bits)
+    w = torch.zeros((T * rows, dim), device=cuda_device)
+    state = torch.zeros(T * rows, device=cuda_device)
+    ops.tbe_backward_fused(w, tro, T, dim, idx, off, B, ones, optimizer="exact_row_wise_adagrad", lr=1.0,
+                           eps=0.0, state=state)
+    small = counts < 1024
+    assert torch.equal(state[small], (counts * counts)[small])
+    touched = counts > 0
+    # w = -lr * g / sqrt(g^2) = -1 on every touched row, 0 elsewhere
+    assert torch.allclose(w[touched][:, 0], torch.full((int(touched.sum()),), -1.0, device=cuda_device), rtol=1e-5)
+    assert not w[~touched].any()
 
 
 @pytest.mark.parametrize("dim", [128, 64, 8])
