@@ -159,13 +159,13 @@ struct OldRow<__half> {
 };
 
 template <typename WT, int OPT, int G, int C, bool SIDE>
-__global__ void __launch_bounds__(256) exact_reduce_kernel(const BwdParams p, const OptParams op,
-                                                           long long n, long long chunk_row0,
-                                                           const unsigned *__restrict__ keys,
-                                                           const unsigned *__restrict__ vals,
-                                                           const unsigned *__restrict__ goff_of,
-                                                           const float *__restrict__ w_of,
-                                                           float4 *__restrict__ partial, int seg_len) {
+__device__ __forceinline__ void exact_reduce_body(const BwdParams &p, const OptParams &op, long long n,
+                                                  long long chunk_row0,
+                                                  const unsigned *__restrict__ keys,
+                                                  const unsigned *__restrict__ vals,
+                                                  const unsigned *__restrict__ goff_of,
+                                                  const float *__restrict__ w_of,
+                                                  float4 *__restrict__ partial, int seg_len) {
     constexpr int BPW = 32 / G;
     constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
     constexpr unsigned kNoKey = 0xffffffffu;   // no chunk-relative row has this id
@@ -361,6 +361,29 @@ __global__ void __launch_bounds__(256) exact_reduce_kernel(const BwdParams p, co
     flush(true);
 }
 
+template <typename WT, int OPT, int G, int C, bool SIDE>
+__global__ void __launch_bounds__(256) exact_reduce_kernel(const BwdParams p, const OptParams op,
+                                                           long long n, long long chunk_row0,
+                                                           const unsigned *__restrict__ keys,
+                                                           const unsigned *__restrict__ vals,
+                                                           const unsigned *__restrict__ goff_of,
+                                                           const float *__restrict__ w_of,
+                                                           float4 *__restrict__ partial, int seg_len) {
+    exact_reduce_body<WT, OPT, G, C, SIDE>(p, op, n, chunk_row0, keys, vals, goff_of, w_of, partial, seg_len);
+}
+// same body compiled for 3 resident CTAs/SM (<= 85 registers; the Adagrad / fp16 variants otherwise
+// use 90-102 and fit only 2): selectable with PB200_EXACT_OCC3=1, dim <= 128 without side arrays
+template <typename WT, int OPT>
+__global__ void __launch_bounds__(256, 3) exact_reduce_kernel_occ3(const BwdParams p, const OptParams op,
+                                                                   long long n, long long chunk_row0,
+                                                                   const unsigned *__restrict__ keys,
+                                                                   const unsigned *__restrict__ vals,
+                                                                   float4 *__restrict__ partial,
+                                                                   int seg_len) {
+    exact_reduce_body<WT, OPT, 32, 1, false>(p, op, n, chunk_row0, keys, vals, nullptr, nullptr, partial,
+                                             seg_len);
+}
+
 // ---- E2 ----------------------------------------------------------------------------------------
 // One CTA per segment; only CTAs whose segment's tail run STARTS a multi-segment run do any work.
 // The 256/G lane groups of the CTA walk the following segments interleaved (group w takes segments
@@ -469,6 +492,10 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
     const SortedPlan pl = plan_exact(p.n_indices, p.num_tables, p.dim, seg_len);
     const int vec4 = p.dim >> 2;
     const bool adagrad = op.optimizer == PB200_OPT_ROWWISE_ADAGRAD;
+    static const int occ3 = [] {
+        const char *e = getenv("PB200_EXACT_OCC3");
+        return e ? atoi(e) : 0;
+    }();
 
     auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
         const long long n = c.n, row0 = c.row0;
@@ -479,7 +506,13 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
     do {                                                                                           \
         const long long per_block = 8ll * (32 / G_);                                               \
         const long long g2 = (n_seg + per_block - 1) / per_block;                                  \
-        if (side && adagrad)                                                                       \
+        if (!side && occ3 && G_ == 32 && C_ == 1 && adagrad)                                       \
+            exact_reduce_kernel_occ3<WT, PB200_OPT_ROWWISE_ADAGRAD>                                \
+                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
+        else if (!side && occ3 && G_ == 32 && C_ == 1)                                             \
+            exact_reduce_kernel_occ3<WT, PB200_OPT_SGD>                                            \
+                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
+        else if (side && adagrad)                                                                  \
             exact_reduce_kernel<WT, PB200_OPT_ROWWISE_ADAGRAD, G_, C_, true>                       \
                 <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, ss.goff_of, ss.w_of, partial, seg_len); \
         else if (side)                                                                             \
