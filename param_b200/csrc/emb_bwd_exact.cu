@@ -22,10 +22,13 @@
 //                            first run if it continues the previous segment's last row, and the
 //                            last run if it continues into the next segment, go to a partial-sum
 //                            buffer instead ([segment][head|tail][dim] fp32).
-//   E2 exact_boundary_kernel one CTA per segment whose tail run STARTS a multi-segment run: tail
-//                            partial + head partials of the following segments while they begin
-//                            with the same row, walked by the CTA's lane groups interleaved (the
-//                            hottest Zipf row spans hundreds of segments), then the update.
+//   E2 exact_boundary_kernel one lane group per segment whose tail run STARTS a multi-segment
+//                            run: tail partial + head partials of the following segments while
+//                            they begin with the same row, then the update; runs longer than 8
+//                            segments go to a work list.
+//   E3 exact_long_run_kernel persistent CTAs, one listed run at a time, the CTA's lane groups
+//                            walking its segments interleaved (the hottest Zipf row spans
+//                            hundreds of segments).
 // Summation order is fixed by the sort (stable radix sort of a fixed pair order) and the segment
 // structure, so two runs on the same inputs give identical bits.
 #include <cuda_fp16.h>
@@ -384,33 +387,35 @@ __global__ void __launch_bounds__(256, 3) exact_reduce_kernel_occ3(const BwdPara
                                              seg_len);
 }
 
-// ---- E2 ----------------------------------------------------------------------------------------
-// One CTA per segment; only CTAs whose segment's tail run STARTS a multi-segment run do any work.
-// The 256/G lane groups of the CTA walk the following segments interleaved (group w takes segments
-// seg+1+w, seg+1+w+NW, ...; U head partials in flight each), so the hottest Zipf row — up to one
-// lookup per bag = 512 segments at batch 65536 — is summed in ~8 dependent steps instead of 64;
-// with one 10 M-row table per chunk that chain was the critical path of the whole chunk
-// (profiles/r01e: 6.3 ms vs 3.7 ms for SORTED at 25 tables).  The group sums are combined through
-// shared memory in group order: the summation order stays fixed, results stay deterministic.
+// ---- E2 / E3 -----------------------------------------------------------------------------------
+// E2: one lane group per segment whose tail run STARTS a multi-segment run.  A run that ends within
+// the next U segments (almost all of them) is finished on the spot: tail partial + head partials of
+// the following segments, then the update.  A longer run — a hot Zipf row spans up to 512 segments
+// at batch 65536 — would be a chain of dependent steps for one lane group, so its first segment is
+// appended to a work list instead.
+// E3: persistent CTAs take the work list; the 256/G lane groups of a CTA walk a run's segments
+// interleaved (group w takes segments seg+1+w, seg+1+w+NW, ...; U head partials in flight each) and
+// combine through shared memory in group order.  The order in which runs are listed varies from
+// launch to launch, the summation order inside a run does not: results stay deterministic.
+// (Measured, profiles/r01e-r01f: E2 alone left 6.3 ms vs 3.7 ms SORTED when every chunk held one
+// 10 M-row table; one CTA per segment instead cost 1.3 ms per 64 tables in CTA launches.)
 template <typename WT, int G, int C>
 __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, const OptParams op,
                                                              long long n, long long chunk_row0,
                                                              const unsigned *__restrict__ keys,
                                                              const float4 *__restrict__ partial,
+                                                             unsigned *__restrict__ worklist,
+                                                             unsigned *__restrict__ work_count,
                                                              int seg_len) {
     constexpr int BPW = 32 / G;
-    constexpr int NW = 8 * BPW;          // lane groups per CTA
     constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
-    __shared__ float4 s_part[256 * C];   // [NW][C*G]
     const int lane = threadIdx.x & 31;
     const int lane_g = lane & (G - 1);
     const int grp = lane / G;
-    const int worker = (threadIdx.x >> 5) * BPW + grp;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int vec4 = p.dim >> 2;
-    const long long seg = blockIdx.x;
+    const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
     const long long s0 = seg * seg_len;
-    // CTA-uniform exits (before the barrier)
     if (s0 >= n) return;
     const long long s1 = min(s0 + (long long)seg_len, n);
     if (s1 >= n) return;                                   // the last segment has no successor
@@ -426,62 +431,134 @@ __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, 
     for (int c = 0; c < C; ++c) {
         const int col = c * G + lane_g;
         col_ok[c] = col < vec4;
-        acc[c] = (worker == 0 && col_ok[c]) ? ld_stream_f4(tail + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[c] = col_ok[c] ? ld_stream_f4(tail + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const long long first = seg + 1 + worker;
-    bool done = !(first * seg_len < n && keys[first * seg_len] == kl);   // most runs end in the next segment
-    for (long long j = first; !done; j += (long long)NW * U) {
-        float4 v[U][C];
-        bool ok[U];
+    float4 v[U][C];
+    bool ok[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long jj = j + (long long)u * NW;
-            const long long pos = jj * seg_len;
-            const bool in = pos < n;
-            ok[u] = in && keys[in ? pos : 0] == kl;
-            // the load is unconditional (keeps U requests in flight); a segment past the run reads
-            // a head partial that is simply not used
-            const float4 *head = partial + ((unsigned long long)(in ? jj : seg) * 2) * (unsigned)vec4;
+    for (int u = 0; u < U; ++u) {
+        const long long jj = seg + 1 + u;
+        const long long pos = jj * seg_len;
+        const bool in = pos < n;
+        ok[u] = in && keys[in ? pos : 0] == kl;
+        // the load is unconditional (keeps U requests in flight); a segment past the run reads a
+        // head partial that is simply not used
+        const float4 *head = partial + ((unsigned long long)(in ? jj : seg) * 2) * (unsigned)vec4;
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                v[u][c] = col_ok[c] ? ld_stream_f4(head + c * G + lane_g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int c = 0; c < C; ++c)
+            v[u][c] = col_ok[c] ? ld_stream_f4(head + c * G + lane_g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (ok[U - 1]) {
+        // all U following segments begin with my row: a long run, left to a whole CTA (E3)
+        if (lane_g == 0) worklist[atomicAdd(work_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    bool done = false;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!done) {
-                if (ok[u]) {
+    for (int u = 0; u < U; ++u) {
+        if (!done) {
+            if (ok[u]) {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        add2b(acc[c].x, acc[c].y, v[u][c].x, v[u][c].y);
-                        add2b(acc[c].z, acc[c].w, v[u][c].z, v[u][c].w);
-                    }
-                } else {
-                    done = true;
+                for (int c = 0; c < C; ++c) {
+                    add2b(acc[c].x, acc[c].y, v[u][c].x, v[u][c].y);
+                    add2b(acc[c].z, acc[c].w, v[u][c].z, v[u][c].w);
                 }
+            } else {
+                done = true;
             }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) s_part[worker * (C * G) + c * G + lane_g] = acc[c];
-    __syncthreads();
-    if (worker != 0) return;
-#pragma unroll 1
-    for (int w = 1; w < NW; ++w) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const float4 x = s_part[w * (C * G) + c * G + lane_g];
-            add2b(acc[c].x, acc[c].y, x.x, x.y);
-            add2b(acc[c].z, acc[c].w, x.z, x.w);
         }
     }
     apply_row_update<WT, G, C>(op, (unsigned long long)chunk_row0 + kl, acc, col_ok, lane_g, vec4,
                                p.dim, gmask);
 }
 
+template <typename WT, int G, int C>
+__global__ void __launch_bounds__(256) exact_long_run_kernel(const BwdParams p, const OptParams op,
+                                                             long long n, long long chunk_row0,
+                                                             const unsigned *__restrict__ keys,
+                                                             const float4 *__restrict__ partial,
+                                                             const unsigned *__restrict__ worklist,
+                                                             const unsigned *__restrict__ work_count,
+                                                             int seg_len) {
+    constexpr int BPW = 32 / G;
+    constexpr int NW = 8 * BPW;          // lane groups per CTA
+    constexpr int U = (C == 1) ? 8 : (C == 2 ? 4 : 2);
+    __shared__ float4 s_part[256 * C];   // [NW][C*G]
+    const int lane = threadIdx.x & 31;
+    const int lane_g = lane & (G - 1);
+    const int grp = lane / G;
+    const int worker = (threadIdx.x >> 5) * BPW + grp;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const int vec4 = p.dim >> 2;
+    bool col_ok[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) col_ok[c] = c * G + lane_g < vec4;
+    const unsigned count = *work_count;
+    for (unsigned item = blockIdx.x; item < count; item += gridDim.x) {
+        const long long seg = worklist[item];
+        const long long s1 = min((seg + 1) * (long long)seg_len, n);
+        const unsigned kl = keys[s1 - 1];
+        float4 acc[C];
+        const float4 *tail = partial + ((unsigned long long)seg * 2 + 1) * (unsigned)vec4;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            acc[c] = (worker == 0 && col_ok[c]) ? ld_stream_f4(tail + c * G + lane_g)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool done = false;
+        for (long long j = seg + 1 + worker; !done; j += (long long)NW * U) {
+            float4 v[U][C];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long jj = j + (long long)u * NW;
+                const long long pos = jj * seg_len;
+                const bool in = pos < n;
+                ok[u] = in && keys[in ? pos : 0] == kl;
+                const float4 *head = partial + ((unsigned long long)(in ? jj : seg) * 2) * (unsigned)vec4;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    v[u][c] = col_ok[c] ? ld_stream_f4(head + c * G + lane_g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!done) {
+                    if (ok[u]) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            add2b(acc[c].x, acc[c].y, v[u][c].x, v[u][c].y);
+                            add2b(acc[c].z, acc[c].w, v[u][c].z, v[u][c].w);
+                        }
+                    } else {
+                        done = true;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_part[worker * (C * G) + c * G + lane_g] = acc[c];
+        __syncthreads();
+        if (worker == 0) {
+#pragma unroll 1
+            for (int w = 1; w < NW; ++w) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float4 x = s_part[w * (C * G) + c * G + lane_g];
+                    add2b(acc[c].x, acc[c].y, x.x, x.y);
+                    add2b(acc[c].z, acc[c].w, x.z, x.w);
+                }
+            }
+            apply_row_update<WT, G, C>(op, (unsigned long long)chunk_row0 + kl, acc, col_ok, lane_g, vec4,
+                                       p.dim, gmask);
+        }
+        __syncthreads();   // s_part is reused by the next item
+    }
+}
+
 constexpr long long kExactPairCap = 32ll << 20;   // keeps the partial-sum buffer at <= 256 MB per set (dim 128)
 
 static SortedPlan plan_exact(long long n_indices, int num_tables, int dim, int seg_len) {
-    return plan_sorted(n_indices, num_tables, true, kExactPairCap, (size_t)2 * (size_t)dim * 4, seg_len);
+    // per segment: head + tail partial sums ([2][dim] fp32) and 8 bytes of work-list space
+    return plan_sorted(n_indices, num_tables, true, kExactPairCap, (size_t)2 * (size_t)dim * 4 + 8, seg_len);
 }
 
 template <typename index_t, typename WT>
@@ -492,16 +569,24 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
     const SortedPlan pl = plan_exact(p.n_indices, p.num_tables, p.dim, seg_len);
     const int vec4 = p.dim >> 2;
     const bool adagrad = op.optimizer == PB200_OPT_ROWWISE_ADAGRAD;
+    // measured (profiles/r01f): 3 resident CTAs/SM speed the Adagrad / fp16 variants up by 6-13 %
     static const int occ3 = [] {
         const char *e = getenv("PB200_EXACT_OCC3");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 1;
     }();
+    const long long n_seg_cap = (pl.max_pairs + seg_len - 1) / seg_len;
 
     auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
         const long long n = c.n, row0 = c.row0;
         const unsigned *ks = c.ks, *vs = c.vs;
         float4 *partial = (float4 *)ss.extra;
         const long long n_seg = (n + seg_len - 1) / seg_len;
+        // behind the partial sums: the long-run work list (one entry per segment at most) + its counter
+        unsigned *worklist = (unsigned *)(ss.extra + (size_t)n_seg_cap * 2 * (size_t)p.dim * 4);
+        unsigned *work_count = worklist + n_seg_cap;
+        if (n_seg > 1) PB200_CUDA_TRY(cudaMemsetAsync(work_count, 0, 4, s));
+        long long g3 = 4ll * sm_count();
+        if (g3 > n_seg) g3 = n_seg;
 #define PB200_EXACT_LAUNCH(G_, C_)                                                                 \
     do {                                                                                           \
         const long long per_block = 8ll * (32 / G_);                                               \
@@ -524,9 +609,12 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
         else                                                                                       \
             exact_reduce_kernel<WT, PB200_OPT_SGD, G_, C_, false>                                  \
                 <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
-        if (n_seg > 1)                                                                             \
-            exact_boundary_kernel<WT, G_, C_><<<(unsigned)n_seg, 256, 0, s>>>(p, op, n, row0, ks,  \
-                                                                             partial, seg_len);   \
+        if (n_seg > 1) {                                                                           \
+            exact_boundary_kernel<WT, G_, C_><<<(unsigned)g2, 256, 0, s>>>(                        \
+                p, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
+            exact_long_run_kernel<WT, G_, C_><<<(unsigned)g3, 256, 0, s>>>(                        \
+                p, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
+        }                                                                                          \
     } while (0)
         if (vec4 <= 4) PB200_EXACT_LAUNCH(4, 1);
         else if (vec4 <= 8) PB200_EXACT_LAUNCH(8, 1);
@@ -535,7 +623,7 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
         else if (vec4 <= 64) PB200_EXACT_LAUNCH(32, 2);
         else PB200_EXACT_LAUNCH(32, 4);
 #undef PB200_EXACT_LAUNCH
-        count_launch(n_seg > 1 ? 2 : 1);
+        count_launch(n_seg > 1 ? 3 : 1);
         PB200_LAUNCH_CHECK();
         return PB200_OK;
     };
