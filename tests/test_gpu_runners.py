@@ -56,3 +56,22 @@ def test_dlrm_pattern_runner_world1(cuda_device):
                 "--json"], 29705)
     rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
     assert rec["iter_time_ms_p50_max_rank"] > 0 and "offset_idx_xchg_ms_p50_max_rank" in rec
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_comms_compute_overlap_runner_world1(cuda_device, direction):
+    """commsComputeBench --kernel emb_lookup (commsComputeBench.py:303-312) without fbgemm_gpu"""
+    out = _run(["-m", "param_b200.comms.pt.comms_compute", "--mode", "comms-compute", "--kernel", "emb_lookup",
+                "--collective", "all_to_all_single", "--b", "1M", "--e", "4M", "--f", "4", "--n", "3", "--w", "1",
+                "--num-compute", "2", "--emb-dim", "64", "--num-embs", "20000", "--batch-size", "256",
+                "--ntables", "4", "--num-emb-tables-batched", "2", "--bag-size", "8", "--direction", direction,
+                "--json"], 29706)
+    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith("{")]
+    assert len(recs) == 2
+    for r in recs:
+        assert r["iter_us"] > 0 and r["comm_dev_us"] > 0 and r["compute_dev_us"] > 0 and r["lookups_per_s"] > 0
+    out = _run(["-m", "param_b200.comms.pt.comms_compute", "--mode", "compute", "--n", "2", "--w", "1",
+                "--num-compute", "3", "--emb-dim", "128", "--num-embs", "5000", "--batch-size", "64",
+                "--ntables", "2", "--bag-size", "4", "--direction", direction, "--json"], 29707)
+    rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+    assert rec["size_bytes"] == 0 and rec["compute_dev_us"] > 0

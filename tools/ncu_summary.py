@@ -28,10 +28,13 @@ cols = []
 for rep in sys.argv[1:]:
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-    name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
-    cols.append((rep.split("/")[-1], name, d))
+    hdr, units = rows[0], rows[1]
+    for k, vals in enumerate(rows[2:]):          # one column per captured launch
+        if len(vals) != len(hdr):
+            continue
+        d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+        name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
+        cols.append((f"{rep.split('/')[-1]} #{k}", name, d))
 print("| metric | " + " | ".join(f"{c[0]}<br>`{c[1][:60]}`" for c in cols) + " |")
 print("|---|" + "---|" * len(cols))
 for key, label in WANT:
