@@ -14,7 +14,16 @@ Ops (all CUDA only; a CPU tensor raises — there is no fallback):
   b200::tbe_forward(Tensor weights, Tensor row_offsets, int dim, Tensor indices, Tensor offsets,
                     int batch, int mode, Tensor? per_sample_weights, int layout) -> Tensor
   b200::tbe_backward_(Tensor(a!) dst, Tensor row_offsets, int dim, Tensor indices, Tensor offsets,
-                      int batch, Tensor grad_out, int layout, float scale, int mode, int algo) -> ()
+                      int batch, Tensor grad_out, int layout, float scale, int mode, int algo) -> Tensor(a!)
+  b200::tbe_backward_fused_(Tensor(a!) weights, Tensor(b!)? state, Tensor row_offsets, int dim,
+                            Tensor indices, Tensor offsets, int batch, Tensor grad_out, int layout,
+                            int mode, Tensor? per_sample_weights, int optimizer, float lr, float eps,
+                            bool stochastic_rounding, int sr_seed) -> Tensor(a!)
+        (in-place ops return the mutated tensor: et_replay's IR builder cannot re-create an op with
+        no output, et_replay_utils.py:171-200)
+        the fused backward + optimizer a DLRM trace records as fbgemm's
+        split_embedding_backward_codegen_*_exact ops; optimizer 1 = exact_sgd, 2 = exact_row_wise_adagrad;
+        weights fp32 or fp16
   b200::regroup_sparse(Tensor lengths, Tensor indices, int world, int tables_local,
                        int local_batch) -> (Tensor, Tensor, Tensor)
 Communication nodes (`record_param_comms` all_to_allv etc.) do not go through op names: et_replay
@@ -28,7 +37,8 @@ from .. import ops as _ops
 
 _MODES = {0: "sum", 1: "mean"}
 _LAYOUT = {0: "BTD", 1: "TBD"}
-_BWD = {0: "auto", 1: "atomic", 2: "sorted"}
+_BWD = {0: "auto", 1: "atomic", 2: "sorted", 3: "exact"}
+_OPT = {1: "exact_sgd", 2: "exact_row_wise_adagrad"}
 
 _lib = torch.library.Library("b200", "DEF")
 _lib.define("embedding_bag(Tensor weight, Tensor indices, Tensor offsets, int mode, "
@@ -36,7 +46,11 @@ _lib.define("embedding_bag(Tensor weight, Tensor indices, Tensor offsets, int mo
 _lib.define("tbe_forward(Tensor weights, Tensor row_offsets, int dim, Tensor indices, Tensor offsets, "
             "int batch, int mode, Tensor? per_sample_weights, int layout) -> Tensor")
 _lib.define("tbe_backward_(Tensor(a!) dst, Tensor row_offsets, int dim, Tensor indices, Tensor offsets, "
-            "int batch, Tensor grad_out, int layout, float scale, int mode, int algo) -> ()")
+            "int batch, Tensor grad_out, int layout, float scale, int mode, int algo) -> Tensor(a!)")
+_lib.define("tbe_backward_fused_(Tensor(a!) weights, Tensor(b!)? state, Tensor row_offsets, int dim, "
+            "Tensor indices, Tensor offsets, int batch, Tensor grad_out, int layout, int mode, "
+            "Tensor? per_sample_weights, int optimizer, float lr, float eps, bool stochastic_rounding, "
+            "int sr_seed) -> Tensor(a!)")
 _lib.define("regroup_sparse(Tensor lengths, Tensor indices, int world, int tables_local, "
             "int local_batch) -> (Tensor, Tensor, Tensor)")
 
@@ -57,6 +71,16 @@ def _tbe_forward(weights, row_offsets, dim, indices, offsets, batch, mode, per_s
 def _tbe_backward_(dst, row_offsets, dim, indices, offsets, batch, grad_out, layout, scale, mode, algo):
     _ops.tbe_backward(dst, row_offsets, row_offsets.numel() - 1, dim, indices, offsets, batch, grad_out,
                       layout=_LAYOUT[layout], scale=scale, mode=_MODES[mode], algo=_BWD[algo])
+    return dst
+
+
+def _tbe_backward_fused_(weights, state, row_offsets, dim, indices, offsets, batch, grad_out, layout, mode,
+                         per_sample_weights, optimizer, lr, eps, stochastic_rounding, sr_seed):
+    _ops.tbe_backward_fused(weights, row_offsets, row_offsets.numel() - 1, dim, indices, offsets, batch,
+                            grad_out, optimizer=_OPT[optimizer], lr=lr, eps=eps, state=state,
+                            layout=_LAYOUT[layout], mode=_MODES[mode], per_sample_weights=per_sample_weights,
+                            stochastic_rounding=stochastic_rounding, sr_seed=sr_seed)
+    return weights
 
 
 def _regroup_sparse(lengths, indices, world, tables_local, local_batch):
@@ -65,6 +89,7 @@ def _regroup_sparse(lengths, indices, world, tables_local, local_batch):
 
 
 for _name, _fn in (("embedding_bag", _embedding_bag), ("tbe_forward", _tbe_forward),
-                   ("tbe_backward_", _tbe_backward_), ("regroup_sparse", _regroup_sparse)):
+                   ("tbe_backward_", _tbe_backward_), ("tbe_backward_fused_", _tbe_backward_fused_),
+                   ("regroup_sparse", _regroup_sparse)):
     _lib.impl(_name, _fn, "CUDA")
     _lib.impl(_name, _fn, "CPU")   # reaches ops._need_cuda -> raises PB200Error: no CPU fallback

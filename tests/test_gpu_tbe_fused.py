@@ -299,3 +299,28 @@ def test_fused_backward_argument_errors(cuda_device):
                                optimizer="exact_row_wise_adagrad")
     with pytest.raises(PB200Error):
         ops.tbe_backward_fused(w, ro, 1, 8, idx, off, 2, torch.ones((2, 8), device=cuda_device), optimizer="adam")
+
+
+def test_et_replay_style_dispatch_of_the_fused_backward(cuda_device, oracle):
+    """et_replay rebuilds an op from node.name + node.op_schema through TorchScript IR
+    (et_replay/et_replay_utils.py:171-212): b200::tbe_backward_fused_ must be callable that way."""
+    import param_b200.et  # noqa: F401
+    ir = """
+graph(%0: Tensor, %1: Tensor?, %2: Tensor, %3: int, %4: Tensor, %5: Tensor, %6: int, %7: Tensor, %8: int,
+      %9: int, %10: Tensor?, %11: int, %12: float, %13: float, %14: bool, %15: int):
+    %output: Tensor = b200::tbe_backward_fused_(%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15)
+    return (%output)
+"""
+    fn = torch._C.CompilationUnit().create_function("b200::tbe_backward_fused_", torch._C.parse_ir(ir))
+    rng = np.random.default_rng(61)
+    T, B, dim = 2, 40, 64
+    tro, arena, offsets, idx = _request(rng, T, B, dim, [90, 30], max_len=7)
+    g = rng.standard_normal((B, T * dim)).astype(np.float32)
+    w = _t(arena, cuda_device)
+    state = torch.zeros(int(tro[-1]), device=cuda_device)
+    ret = fn(w, state, _t(tro, cuda_device), dim, _t(idx, cuda_device), _t(offsets, cuda_device), B,
+             _t(g, cuda_device), 0, 0, None, 2, 0.05, 1e-8, False, 0)
+    assert ret.data_ptr() == w.data_ptr()
+    dense = oracle.tbe_bwd(int(tro[-1]), tro, dim, idx, offsets, B, g, dtype=np.float64)
+    want, m_want = oracle.fused_optimizer_step(arena, dense, "exact_row_wise_adagrad", lr=0.05, eps=1e-8)
+    assert _rel(w.cpu().numpy(), want) <= RTOL and _rel(state.cpu().numpy(), m_want) <= RTOL
