@@ -387,170 +387,12 @@ __global__ void __launch_bounds__(256, 3) exact_reduce_kernel_occ3(const BwdPara
                                              seg_len);
 }
 
-// ---- E1, slim form (dim <= 128 rows: one warp = one lane group, no side arrays) -----------------
-// Same decomposition and the same arithmetic as exact_reduce_body, with the per-entry bookkeeping
-// taken out of the common path: the batch is classified from its keys BEFORE the loads are issued.
-//   uniform batch (8 valid entries, one key, continuing the running row — almost every batch of a
-//   hot Zipf row): 8 gradient loads + ONE state / old-row prefetch for the last entry, no predicates;
-//   mixed batch: per-entry "may end a run" predicates as before, but a flush takes the prefetch of
-//   the entry just before it by a compile-time index (the previous batch's last entry is carried).
-// profiles/r01g: the general body executes 51 warp instructions per sorted entry (ISETP/SEL/MOV
-// bookkeeping, 2 spills under the 85-register cap) vs 19 for the SORTED reduce.
-template <typename WT, int OPT>
-__global__ void __launch_bounds__(256, 3) exact_reduce_slim_kernel(const BwdParams p, const OptParams op,
-                                                                   long long n, long long chunk_row0,
-                                                                   const unsigned *__restrict__ keys,
-                                                                   const unsigned *__restrict__ vals,
-                                                                   float4 *__restrict__ partial,
-                                                                   int seg_len) {
-    constexpr int U = 8;
-    constexpr unsigned kNoKey = 0xffffffffu;
-    constexpr bool kAdagrad = OPT == PB200_OPT_ROWWISE_ADAGRAD;
-    constexpr bool kOldW = OldRow<WT>::kNeeded;
-    using OldW = typename OldRow<WT>::raw;
-    const int lane = threadIdx.x & 31;
-    const int vec4 = p.dim >> 2;
-    const bool col_ok = lane < vec4;
-    const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long s0 = seg * seg_len;
-    if (s0 >= n) return;                                   // warp-uniform
-    const long long s1 = min(s0 + (long long)seg_len, n);
-    const int my_n = (int)(s1 - s0);
-    const bool head_cont = s0 > 0 && keys[s0 - 1] == keys[s0];
-    const bool tail_cont = s1 < n && keys[s1] == keys[s1 - 1];
-    bool first_run = true;
-    const float4 *colp = (const float4 *)p.grad_out + (col_ok ? lane : 0);
-    const unsigned col = col_ok ? (unsigned)lane : 0u;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned cur_key = kNoKey;
-    float carry_state = 0.f;     // prefetch taken with the latest processed entry
-    OldW carry_w{};
-
-    auto flush = [&](bool last, float state_old, const OldW &w_old) {
-        if (cur_key != kNoKey) {
-            const int which = (first_run && head_cont) ? 0 : ((last && tail_cont) ? 1 : -1);
-            if (which >= 0) {
-                if (col_ok) partial[((unsigned long long)seg * 2 + which) * (unsigned)vec4 + lane] = acc;
-            } else {
-                const unsigned long long row = (unsigned long long)chunk_row0 + cur_key;
-                float mult = op.lr;
-                if (kAdagrad) {
-                    float ss = 0.f;
-                    if (col_ok) {
-                        ss = fmaf(acc.x, acc.x, ss);
-                        ss = fmaf(acc.y, acc.y, ss);
-                        ss = fmaf(acc.z, acc.z, ss);
-                        ss = fmaf(acc.w, acc.w, ss);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                    const float m = state_old + ss / (float)p.dim;
-                    if (lane == 0) op.state[row] = m;
-                    mult = op.lr / (sqrtf(m) + op.eps);
-                }
-                if (col_ok) {
-                    const unsigned long long v = row * (unsigned)vec4 + (unsigned)lane;
-                    if constexpr (kOldW) {
-                        const uint2 raw = w_old;
-                        const float2 lo = __half22float2(*(const __half2 *)&raw.x);
-                        const float2 hi = __half22float2(*(const __half2 *)&raw.y);
-                        float4 w = make_float4(lo.x, lo.y, hi.x, hi.y);
-                        w.x = fmaf(-mult, acc.x, w.x);
-                        w.y = fmaf(-mult, acc.y, w.y);
-                        w.z = fmaf(-mult, acc.z, w.z);
-                        w.w = fmaf(-mult, acc.w, w.w);
-                        Row4<WT>::store(op.weights, v, w, op);
-                    } else {
-                        float4 d = acc;
-                        d.x *= -mult; d.y *= -mult; d.z *= -mult; d.w *= -mult;
-                        red_add_f4((float4 *)op.weights + v, d);
-                    }
-                }
-            }
-            first_run = false;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto prefetch_state = [&](unsigned key) -> float {
-        return kAdagrad ? op.state[(unsigned long long)chunk_row0 + key] : 0.f;
-    };
-    auto prefetch_row = [&](unsigned key) -> OldW {
-        return OldRow<WT>::load(op.weights, ((unsigned long long)chunk_row0 + key) * (unsigned)vec4 + col);
-    };
-
-    for (int base = 0; base < my_n; base += 32) {
-        unsigned my_key = 0, my_goff = 0;
-        if (base + lane < my_n) {
-            my_key = keys[s0 + base + lane];
-            my_goff = vals[s0 + base + lane];
-        }
-        const int cnt = min(32, my_n - base);
-        for (int j0 = 0; j0 < cnt; j0 += U) {
-            const int nvb = min(U, cnt - j0);              // valid entries of this batch (warp-uniform)
-            unsigned kk[U], goff[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                kk[u] = __shfl_sync(0xffffffffu, my_key, j0 + u);
-                goff[u] = __shfl_sync(0xffffffffu, my_goff, j0 + u);
-            }
-            float4 v[U];
-            if (nvb == U && kk[U - 1] == kk[0] && (kk[0] == cur_key || cur_key == kNoKey)) {
-                // uniform batch: keys are sorted, first == last => all equal
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = ld_row_f4(colp + goff[u]);
-                const float st = prefetch_state(kk[0]);
-                OldW ow{};
-                if constexpr (kOldW) ow = prefetch_row(kk[0]);
-                cur_key = kk[0];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    add2b(acc.x, acc.y, v[u].x, v[u].y);
-                    add2b(acc.z, acc.w, v[u].z, v[u].w);
-                }
-                carry_state = st;
-                carry_w = ow;
-            } else {
-                float st[U];
-                OldW ow[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    v[u] = ld_row_f4(colp + goff[u]);      // entries past nvb alias gradient row 0
-                    // entry u can end a run: it is valid and the next one is outside the batch or differs
-                    const bool ends = (u < nvb) && (u + 1 >= nvb || kk[u + 1 < U ? u + 1 : u] != kk[u]);
-                    st[u] = 0.f;
-                    ow[u] = OldW{};
-                    if (ends) {
-                        st[u] = prefetch_state(kk[u]);
-                        if constexpr (kOldW) ow[u] = prefetch_row(kk[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (u < nvb) {
-                        if (kk[u] != cur_key) {
-                            // the run that ends here ended with the previous entry
-                            if (u == 0)
-                                flush(false, carry_state, carry_w);
-                            else
-                                flush(false, st[u > 0 ? u - 1 : 0], ow[u > 0 ? u - 1 : 0]);
-                            cur_key = kk[u];
-                        }
-                        add2b(acc.x, acc.y, v[u].x, v[u].y);
-                        add2b(acc.z, acc.w, v[u].z, v[u].w);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (u == nvb - 1) {
-                        carry_state = st[u];
-                        carry_w = ow[u];
-                    }
-                }
-            }
-        }
-    }
-    flush(true, carry_state, carry_w);
-}
+// (A "slim" E1 that classifies each batch from its keys BEFORE issuing the loads — uniform batches
+// with one prefetch and no predicates, mixed batches with compile-time-indexed prefetches — executed
+// 30 % fewer warp instructions but ran slower: 9.77 vs 8.41 ms Adagrad at 64 tables, 73 ms for fp16.
+// Duplicating the load sequences and the inlined flush grew the kernel to 7 184 SASS instructions
+// (instruction-cache misses, issue slots 30 % busy) and to 156-316 B of spills; removed, evidence in
+// profiles/r01i_*.)
 
 // ---- E2 / E3 -----------------------------------------------------------------------------------
 // E2: one lane group per segment whose tail run STARTS a multi-segment run.  A run that ends within
@@ -739,10 +581,6 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
         const char *e = getenv("PB200_EXACT_OCC3");
         return e ? atoi(e) : 1;
     }();
-    static const int slim = [] {
-        const char *e = getenv("PB200_EXACT_SLIM");   // slim E1 for dim <= 128 rows without side arrays
-        return e ? atoi(e) : 0;
-    }();
     const long long n_seg_cap = (pl.max_pairs + seg_len - 1) / seg_len;
 
     auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
@@ -760,13 +598,7 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
     do {                                                                                           \
         const long long per_block = 8ll * (32 / G_);                                               \
         const long long g2 = (n_seg + per_block - 1) / per_block;                                  \
-        if (!side && slim && G_ == 32 && C_ == 1 && adagrad)                                       \
-            exact_reduce_slim_kernel<WT, PB200_OPT_ROWWISE_ADAGRAD>                                \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
-        else if (!side && slim && G_ == 32 && C_ == 1)                                             \
-            exact_reduce_slim_kernel<WT, PB200_OPT_SGD>                                            \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
-        else if (!side && occ3 && G_ == 32 && C_ == 1 && adagrad)                                  \
+        if (!side && occ3 && G_ == 32 && C_ == 1 && adagrad)                                       \
             exact_reduce_kernel_occ3<WT, PB200_OPT_ROWWISE_ADAGRAD>                                \
                 <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
         else if (!side && occ3 && G_ == 32 && C_ == 1)                                             \

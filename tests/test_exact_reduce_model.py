@@ -199,48 +199,3 @@ def test_prefetched_state_always_belongs_to_the_flushed_row(G, U):
             keys = np.sort(rng.integers(0, n_keys, size=n)).tolist()
             flushed = _e1_prefetch_model(keys, G, U)
             assert flushed == sorted(set(keys))
-
-
-def _e1_slim_model(keys, U=8):
-    """exact_reduce_slim_kernel: the batch is classified before the loads; a flush takes the prefetch of
-    the entry just before it (compile-time index) or the carried one of the previous batch."""
-    my_n = len(keys)
-    cur_key, carry, flushed = None, None, []
-
-    def flush(state_old):
-        if cur_key is not None:
-            assert state_old == ("state-of", cur_key), (cur_key, state_old)
-            flushed.append(cur_key)
-
-    for base in range(0, my_n, 32):
-        cnt = min(32, my_n - base)
-        for j0 in range(0, cnt, U):
-            nvb = min(U, cnt - j0)
-            kk = [keys[base + j0 + u] if u < nvb else 0 for u in range(U)]
-            if nvb == U and kk[U - 1] == kk[0] and (kk[0] == cur_key or cur_key is None):
-                cur_key = kk[0]
-                carry = ("state-of", kk[0])
-            else:
-                st = []
-                for u in range(U):
-                    ends = (u < nvb) and (u + 1 >= nvb or kk[u + 1 if u + 1 < U else u] != kk[u])
-                    st.append(("state-of", kk[u]) if ends else None)
-                for u in range(U):
-                    if u < nvb:
-                        if kk[u] != cur_key:
-                            flush(carry if u == 0 else st[u - 1])
-                            cur_key = kk[u]
-                for u in range(U):
-                    if u == nvb - 1:
-                        carry = st[u]
-    flush(carry)
-    return flushed
-
-
-def test_slim_e1_flushes_with_the_prefetch_of_the_right_row():
-    rng = np.random.default_rng(77)
-    for n in (1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40, 64, 100, 128):
-        for n_keys in (1, 2, 3, 5, 40, 500):
-            for _ in range(5):
-                keys = np.sort(rng.integers(0, n_keys, size=n)).tolist()
-                assert _e1_slim_model(keys) == sorted(set(keys))
