@@ -136,7 +136,7 @@ def run(argv=None):
             if a.collective == "all_to_allv":
                 ca.ipTensor_split = [numel // world] * world
                 ca.opTensor_split = [numel // world] * world
-        comm_t, comp_t = _DeviceTimer(), _DeviceTimer()
+        comm_t, comp_t, span_t = _DeviceTimer(), _DeviceTimer(), _DeviceTimer()
         elapsed = 0.0
         for it in range(a.w + a.n):
             if it == a.w:
@@ -144,9 +144,11 @@ def run(argv=None):
                 elapsed = 0.0
                 comm_t.reset()
                 comp_t.reset()
+                span_t.reset()
             cur = torch.cuda.current_stream(dev)
             compute_stream.wait_stream(cur)          # both legs start from the same point
             start = time.monotonic()
+            span_t.start(cur)                        # device time from the common start to the join of both legs
             if comms_on:
                 comm_t.start(cur)
                 for _ in range(a.num_coll):
@@ -158,23 +160,29 @@ def run(argv=None):
                 for _ in range(a.num_compute):
                     be.emb_lookup(ca)
                 comp_t.stop(compute_stream)
+            cur.wait_stream(compute_stream)
+            span_t.stop(cur)
             torch.cuda.synchronize(dev)
             dist.barrier(device_ids=[local_rank])    # sync_barrier(desc="runColl_sync")
             elapsed += time.monotonic() - start
             comm_t.collect()
             comp_t.collect()
+            span_t.collect()
         it_us = elapsed / a.n * 1e6
         comm_us, comp_us = comm_t.total_ms / a.n * 1e3, comp_t.total_ms / a.n * 1e3
-        t = torch.tensor([it_us, comm_us, comp_us], device=dev, dtype=torch.float64)
+        span_us = span_t.total_ms / a.n * 1e3
+        t = torch.tensor([it_us, comm_us, comp_us, span_us], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        it_us, comm_us, comp_us = (float(x) for x in t)
+        it_us, comm_us, comp_us, span_us = (float(x) for x in t)
         nbytes = numel * es if comms_on else 0
         alg = nbytes * a.num_coll / (it_us * 1e-6) / 1e9 if comms_on else 0.0       # getAlgBW over the iteration
         bus = be.getBusBW(a.collective, alg, ca) if comms_on else 0.0
-        # 1.0 = the shorter leg is completely hidden behind the longer one, 0.0 = the legs ran back to back
-        overlap = (comm_us + comp_us - it_us) / min(comm_us, comp_us) if comms_on and min(comm_us, comp_us) > 0 else 0.0
+        # device-side: 1.0 = the shorter leg is completely hidden behind the longer one, 0.0 = the legs
+        # ran back to back (iter_us is wall clock and also holds the host launches and the barrier)
+        overlap = (comm_us + comp_us - span_us) / min(comm_us, comp_us) if comms_on and min(comm_us, comp_us) > 0 else 0.0
         rec = {"mode": a.mode, "kernel": a.kernel, "collective": a.collective if comms_on else None, "world": world,
                "size_bytes": nbytes, "iter_us": it_us, "comm_dev_us": comm_us, "compute_dev_us": comp_us,
+               "dev_span_us": span_us,
                "overlap": overlap, "algbw_gbs": alg, "busbw_gbs": bus,
                "lookups_per_s": world * lookups_per_compute * a.num_compute / (it_us * 1e-6),
                "direction": a.direction, "emb_optimizer": a.emb_optimizer}
