@@ -75,3 +75,11 @@ def test_comms_compute_overlap_runner_world1(cuda_device, direction):
                 "--ntables", "2", "--bag-size", "4", "--direction", direction, "--json"], 29707)
     rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
     assert rec["size_bytes"] == 0 and rec["compute_dev_us"] > 0
+
+
+def test_aten_embedding_bag_override_in_its_own_process(cuda_device):
+    """param_b200.et.aten_override: stock nn.EmbeddingBag (what a captured DLRM trace replays as
+    aten::embedding_bag / aten::_embedding_bag_backward, SURVEY App. D) lands on the B200 kernels and
+    reproduces the torch-CPU goldens.  Own process: the registration is process-wide."""
+    out = _run([str(ROOT / "tests" / "helpers" / "aten_override_check.py")], 29708)
+    assert "ATEN-OVERRIDE-OK" in out

@@ -238,6 +238,14 @@ def test_et_replay_builds_b200_ops_from_name_and_schema():
                               "Tensor offsets, int batch, int mode, Tensor? per_sample_weights, int layout) -> Tensor", 9, 1),
         "b200::regroup_sparse": ("b200::regroup_sparse(Tensor lengths, Tensor indices, int world, int tables_local, "
                                  "int local_batch) -> (Tensor, Tensor, Tensor)", 5, 3),
+        "b200::tbe_backward_": ("b200::tbe_backward_(Tensor(a!) dst, Tensor row_offsets, int dim, Tensor indices, "
+                                "Tensor offsets, int batch, Tensor grad_out, int layout, float scale, int mode, "
+                                "int algo) -> Tensor(a!)", 11, 1),
+        "b200::tbe_backward_fused_": ("b200::tbe_backward_fused_(Tensor(a!) weights, Tensor(b!)? state, "
+                                      "Tensor row_offsets, int dim, Tensor indices, Tensor offsets, int batch, "
+                                      "Tensor grad_out, int layout, int mode, Tensor? per_sample_weights, "
+                                      "int optimizer, float lr, float eps, bool stochastic_rounding, int sr_seed) "
+                                      "-> Tensor(a!)", 16, 1),
     }
     for name, (schema, n_in, n_out) in schemas.items():
         # the schema string must be the one the dispatcher really holds (what an ET capture records)
@@ -328,3 +336,29 @@ def test_position_coded_data_check_matches_c10d_two_ranks_gloo(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_payload_worker, args=(2, 29681, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").read_text() == "1" and (tmp_path / "ok1").read_text() == "1"
+
+
+def test_aten_override_registers_cuda_kernels_only():
+    """param_b200.et.aten_override (own process: the registration is process-wide) replaces the CUDA
+    kernels of the three aten EmbeddingBag ops and leaves the CPU path alone."""
+    import subprocess
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "import param_b200.et.aten_override\n"
+        "for op in ('_embedding_bag', '_embedding_bag_forward_only', '_embedding_bag_backward'):\n"
+        "    d = torch._C._dispatch_dump('aten::' + op)\n"
+        "    cuda = [l for l in d.splitlines() if l.startswith('CUDA:')]\n"
+        "    assert len(cuda) == 1 and 'aten_override.py' in cuda[0], (op, cuda)\n"
+        "    cpu = [l for l in d.splitlines() if l.startswith('CPU:')]\n"
+        "    assert len(cpu) == 1 and 'aten_override.py' not in cpu[0], (op, cpu)\n"
+        "e = torch.nn.EmbeddingBag(10, 4, mode='sum')\n"
+        "o = e(torch.tensor([1, 2, 3, 4]), torch.tensor([0, 2]))\n"
+        "o.sum().backward()\n"
+        "assert e.weight.grad[1].tolist() == [1.0] * 4\n"
+        "print('OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    import json
+    cfg = json.loads((ROOT / "param_b200" / "et" / "replay-config-b200-aten.json").read_text())
+    assert cfg["import modules"] == ["param_b200.et", "param_b200.et.aten_override"]
