@@ -10,7 +10,7 @@
 // ATOMIC : one lane group per bag; the bag's gradient row is read once (16 B per lane) and
 //          red.global.add.v4.f32 is issued per lookup.  Summation order across bags is not fixed.
 // SORTED : per chunk of tables — (1) build (arena row, bag) pairs, (2) cub radix sort by row,
-//          (3) one lane group per 128 sorted entries accumulates runs of equal rows in registers and
+//          (3) one lane group per 256 sorted entries accumulates runs of equal rows in registers and
 //          issues ONE red per (segment, row).  Under Zipf skew ~87 % of the lookups of a table-batch
 //          are duplicates, so the number of L2 read-modify-writes drops ~8x and hot rows no longer
 //          serialise on one L2 slice; rows wholly inside a segment are updated exactly once

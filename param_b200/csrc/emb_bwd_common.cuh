@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(256) build_pairs_kernel(const BwdParams p, lon
     }
 }
 
-constexpr int kSeg = 128;  // sorted entries per lane group; measured: 128 beats 64 by 4.5 % under Zipf, costs 1.6 % under uniform indices
+// sorted entries per lane group.  Measured at 64 tables (profiles/README.md, r01e_variant_*_seg256.log): 128 beats 64
+// by 4.5 % under Zipf and costs 1.6 % under uniform indices; 256 beats 128 by another 3.8 % under Zipf (SORTED 6.18 ->
+// 5.94 ms, EXACT 6.78 -> 6.34 ms: half as many boundary runs and partial sums) and costs 0.9 % under uniform indices.
+constexpr int kSeg = 256;
 
 __device__ __forceinline__ void add2b(float &a0, float &a1, float b0, float b1) {
     asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; "

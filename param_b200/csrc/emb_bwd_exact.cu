@@ -16,7 +16,7 @@
 // A non-linear update needs the COMPLETE gradient of a row, so the "one red per (segment, row)" of
 // the SORTED variant (emb_bwd.cu) is not enough.  Per chunk of tables, after the same pair build +
 // radix sort (emb_bwd_common.cuh):
-//   E1 exact_reduce_kernel   one lane group per 128 sorted entries, runs of equal rows summed in
+//   E1 exact_reduce_kernel   one lane group per 256 sorted entries, runs of equal rows summed in
 //                            registers.  A run that lies wholly inside the segment is final: the
 //                            optimizer is applied on the spot (row read once, written once).  The
 //                            first run if it continues the previous segment's last row, and the
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256, 3) exact_reduce_kernel_occ3(const BwdPara
 // ---- E2 / E3 -----------------------------------------------------------------------------------
 // E2: one lane group per segment whose tail run STARTS a multi-segment run.  A run that ends within
 // the next U segments (almost all of them) is finished on the spot: tail partial + head partials of
-// the following segments, then the update.  A longer run — a hot Zipf row spans up to 512 segments
+// the following segments, then the update.  A longer run — a hot Zipf row spans up to 256 segments
 // at batch 65536 — would be a chain of dependent steps for one lane group, so its first segment is
 // appended to a work list instead.
 // E3: persistent CTAs take the work list; the 256/G lane groups of a CTA walk a run's segments
