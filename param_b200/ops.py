@@ -184,7 +184,10 @@ _scratch_cache: dict = {}
 
 
 def _scratch(device, nbytes: int) -> torch.Tensor:
-    key = (device.type, device.index)
+    """Grow-only scratch buffer, one per (device, current stream): kernels of two streams never share
+    one, and the caching allocator hands a replaced buffer back only in the order of the stream it was
+    allocated on."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
