@@ -362,3 +362,41 @@ def test_aten_override_registers_cuda_kernels_only():
     import json
     cfg = json.loads((ROOT / "param_b200" / "et" / "replay-config-b200-aten.json").read_text())
     assert cfg["import modules"] == ["param_b200.et", "param_b200.et.aten_override"]
+
+
+def test_fused_backward_and_fp16_paths_refuse_cpu_tensors_and_bad_arguments():
+    """no CPU fallback anywhere: the new entries raise PB200Error before touching the library"""
+    from param_b200 import ops
+    from param_b200._cabi import PB200Error
+    w = torch.zeros(10, 8)
+    ro = torch.tensor([0, 10])
+    idx, off, g = torch.zeros(4, dtype=torch.int64), torch.tensor([0, 2, 4]), torch.ones(2, 8)
+    with pytest.raises(PB200Error, match="CUDA tensors only"):
+        ops.tbe_backward_fused(w, ro, 1, 8, idx, off, 2, g)
+    with pytest.raises(PB200Error, match="CUDA tensors only"):
+        ops.tbe_forward(ops.TableArena(w.half(), ro, [10], 8), idx, off, 2)
+    with pytest.raises(PB200Error):
+        ops.TableArena.allocate([10], 8, "cpu", dtype=torch.bfloat16)        # fp32 / fp16 tables only
+    assert ops._OPTIMIZER["exact_row_wise_adagrad"] == ops.OPT_ROWWISE_ADAGRAD == 2
+    assert ops._OPTIMIZER["exact_sgd"] == ops.OPT_SGD == 1                     # values of include/param_b200.h
+    from param_b200.compute.tbe import B200TBE
+    with pytest.raises(PB200Error):
+        B200TBE([(10, 8), (10, 16)], device="cpu")                            # mixed dims
+    with pytest.raises(PB200Error):
+        B200TBE([(10, 8)], device="cpu", weights_precision="int8")
+    with pytest.raises(PB200Error):
+        B200TBE([(10, 8)], device="cpu", optimizer="adam")
+    with pytest.raises(PB200Error):
+        B200TBE([(10, 8)], device="cpu", optimizer="exact_row_wise_adagrad", bwd_algo="sorted")
+
+
+def test_comms_compute_runner_flags_match_the_reference_names():
+    """commsComputeBench flag names and defaults (commsComputeBench.py:37-136)"""
+    from param_b200.comms.pt.comms_compute import _args
+    a = _args([])
+    assert (a.mode, a.kernel, a.num_compute, a.emb_dim, a.num_embs, a.batch_size, a.num_emb_tables_per_device,
+            a.num_emb_tables_batched, a.bag_size) == ("comms-compute", "emb_lookup", 100, 128, 100000, 512, 8, -1, 20)
+    a = _args(["--mode", "compute", "--ntables", "4", "--num-compute-per-iteration", "7", "--begin-size", "2M"])
+    assert a.mode == "compute" and a.num_emb_tables_per_device == 4 and a.num_compute == 7 and a.b == "2M"
+    with pytest.raises(SystemExit):
+        _args(["--kernel", "gemm"])            # dense kernels are outside the hot path
