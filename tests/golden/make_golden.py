@@ -18,6 +18,13 @@ fixtures are produced by running the reference's own call sites here:
                         train/comms/pt/pytorch_dist_backend.py:336-351) and the reference's own
                         All2Allv_Req / All2Allv_Wait autograd Functions + torch.cat
                         (train/comms/pt/dlrm.py:86-218, 858-878, 1253), forward and backward.
+  tbe_optim_torch.npz   the reference's TBE benchmark step — forward, create_grad = ones_like, backward with
+                        the optimizer fused in (train/compute/python/workloads/pytorch/
+                        split_table_batched_embeddings_ops.py:311-324) — computed WITHOUT fbgemm_gpu (absent) by
+                        the per-table nn.EmbeddingBag loop + torch.optim.SGD / torch.optim.Adagrad.  With a
+                        ones gradient every row gradient is constant along the row, where fbgemm's rowwise
+                        Adagrad (mean over the row of g^2) coincides with the elementwise torch.optim.Adagrad.
+                        Generate alone with:  python tests/golden/make_golden.py tbe_optim
 """
 from __future__ import annotations
 
@@ -242,7 +249,52 @@ def gen_a2a():
     print("a2a_gloo_ref.npz")
 
 
+def gen_tbe_optim():
+    """3 training steps of a 3-table TBE op on CPU with torch only (no oracle code involved)."""
+    torch.manual_seed(7)
+    rng = np.random.default_rng(20261017)
+    rows, dim, B, lr, eps, steps = [60, 20, 150], 32, 32, 0.05, 1.0e-8, 3
+    T = len(rows)
+    w0 = [torch.randn(r, dim) * 0.1 for r in rows]
+    out = {"rows": np.array(rows), "dim": dim, "batch": B, "lr": lr, "eps": eps, "steps": steps,
+           "w0": torch.cat(w0).numpy()}
+    requests = []
+    for s in range(steps):
+        lens = rng.integers(0, 9, size=T * B)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        idx = np.concatenate([rng.integers(0, rows[t], size=int(lens[t * B:(t + 1) * B].sum()))
+                              for t in range(T)]).astype(np.int64)
+        requests.append((idx, offsets))
+        out[f"s{s}_indices"], out[f"s{s}_offsets"] = idx, offsets
+    for name, make_opt in (("sgd", lambda ps: torch.optim.SGD(ps, lr=lr)),
+                           ("adagrad", lambda ps: torch.optim.Adagrad(ps, lr=lr, eps=eps,
+                                                                      initial_accumulator_value=0.0))):
+        embs = [nn.EmbeddingBag(r, dim, mode="sum", _weight=w.clone()) for r, w in zip(rows, w0)]
+        opt = make_opt([e.weight for e in embs])
+        for s, (idx, offsets) in enumerate(requests):
+            opt.zero_grad()
+            pooled = []
+            for t, e in enumerate(embs):                     # the per-table loop of dlrm.py:363-388
+                lo, hi = offsets[t * B], offsets[(t + 1) * B]
+                pooled.append(e(torch.from_numpy(idx[lo:hi]), torch.from_numpy(offsets[t * B:(t + 1) * B] - lo)))
+            fwd_out = torch.cat(pooled, dim=1)               # [B, T*dim], the TBE output layout
+            out[f"{name}_s{s}_out"] = fwd_out.detach().numpy().copy()
+            fwd_out.backward(torch.ones_like(fwd_out))       # create_grad (:315-316) + backward (:318-324)
+            opt.step()
+            out[f"{name}_s{s}_w"] = torch.cat([e.weight.detach() for e in embs]).numpy().copy()
+        if name == "adagrad":
+            # elementwise accumulator; constant along a row here, so column 0 is fbgemm's rowwise state
+            out["adagrad_state"] = torch.cat([opt.state[e.weight]["sum"][:, 0] for e in embs]).numpy().copy()
+            acc = torch.cat([opt.state[e.weight]["sum"] for e in embs])
+            assert bool((acc == acc[:, :1]).all()), "the accumulator must be constant along a row"
+    np.savez_compressed(HERE / "tbe_optim_torch.npz", **out)
+    print("wrote tbe_optim_torch.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tbe_optim":      # torch only: no reference import needed
+        gen_tbe_optim()
+        raise SystemExit(0)
     if not REF.exists():
         raise SystemExit("/root/reference not present: golden vectors can only be regenerated "
                          "in the build container")
@@ -250,3 +302,4 @@ if __name__ == "__main__":
     gen_init_indices()
     gen_dlrm_sparse()
     gen_a2a()
+    gen_tbe_optim()

@@ -324,3 +324,26 @@ graph(%0: Tensor, %1: Tensor?, %2: Tensor, %3: int, %4: Tensor, %5: Tensor, %6: 
     dense = oracle.tbe_bwd(int(tro[-1]), tro, dim, idx, offsets, B, g, dtype=np.float64)
     want, m_want = oracle.fused_optimizer_step(arena, dense, "exact_row_wise_adagrad", lr=0.05, eps=1e-8)
     assert _rel(w.cpu().numpy(), want) <= RTOL and _rel(state.cpu().numpy(), m_want) <= RTOL
+
+
+def test_tbe_training_steps_match_torch_optim_golden(cuda_device, golden_dir):
+    """tests/golden/tbe_optim_torch.npz — 3 steps of the reference's TBE benchmark loop (forward,
+    create_grad = ones_like, backward with the fused optimizer; split_table_batched_embeddings_ops.py:311-324)
+    computed with torch only (per-table nn.EmbeddingBag + torch.optim.SGD / Adagrad; with a ones gradient
+    rowwise Adagrad == elementwise Adagrad).  B200TBE must follow it step for step: 1e-5 relative."""
+    from param_b200.compute.tbe import B200TBE
+    d = np.load(golden_dir / "tbe_optim_torch.npz")
+    rows, dim, B = [int(r) for r in d["rows"]], int(d["dim"]), int(d["batch"])
+    lr, eps = float(d["lr"]), float(d["eps"])
+    for name, optimizer in (("sgd", "exact_sgd"), ("adagrad", "exact_row_wise_adagrad")):
+        for bwd_algo in (("exact", "sorted") if name == "sgd" else ("exact",)):
+            op = B200TBE([(r, dim) for r in rows], optimizer=optimizer, learning_rate=lr, eps=eps,
+                         device=cuda_device, bwd_algo=bwd_algo)
+            op.weights.copy_(_t(d["w0"], cuda_device))
+            for s in range(int(d["steps"])):
+                out = op.forward(_t(d[f"s{s}_indices"], cuda_device), _t(d[f"s{s}_offsets"], cuda_device), None)
+                np.testing.assert_allclose(out.detach().cpu().numpy(), d[f"{name}_s{s}_out"], rtol=RTOL, atol=1e-6)
+                out.backward(torch.ones_like(out))
+                assert _rel(op.weights.cpu().numpy(), d[f"{name}_s{s}_w"]) <= RTOL, (name, bwd_algo, s)
+            if name == "adagrad":
+                assert _rel(op.momentum1.cpu().numpy(), d["adagrad_state"]) <= RTOL

@@ -150,3 +150,25 @@ def test_rowwise_adagrad_restatement_matches_torch_adagrad_on_row_constant_gradi
     opt2.step()
     got2, _ = oracle.fused_optimizer_step(w1, g1, "exact_sgd", lr=lr)
     np.testing.assert_allclose(got2, tw2.detach().numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_training_steps_match_torch_optim_golden(oracle, golden_dir):
+    """tests/golden/tbe_optim_torch.npz: 3 steps of the reference's TBE benchmark loop (forward, ones
+    gradient, fused optimizer) computed with torch only — per-table nn.EmbeddingBag + torch.optim.SGD /
+    Adagrad.  The oracle's forward + dense backward + fused_optimizer_step must reproduce it."""
+    d = np.load(golden_dir / "tbe_optim_torch.npz")
+    rows, dim, B = d["rows"], int(d["dim"]), int(d["batch"])
+    lr, eps = float(d["lr"]), float(d["eps"])
+    tro = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    for name, optimizer in (("sgd", "exact_sgd"), ("adagrad", "exact_row_wise_adagrad")):
+        w, m = d["w0"].astype(np.float64), None
+        for s in range(int(d["steps"])):
+            idx, off = d[f"s{s}_indices"], d[f"s{s}_offsets"]
+            out = oracle.tbe_fwd(w.astype(np.float32), tro, dim, idx, off, B)
+            np.testing.assert_allclose(out, d[f"{name}_s{s}_out"], rtol=1e-5, atol=1e-6)
+            g = oracle.tbe_bwd(int(tro[-1]), tro, dim, idx, off, B, np.ones((B, len(rows) * dim), np.float32),
+                               dtype=np.float64)
+            w, m = oracle.fused_optimizer_step(w, g, optimizer, lr=lr, eps=eps, state=m)
+            np.testing.assert_allclose(w, d[f"{name}_s{s}_w"], rtol=1e-5, atol=1e-6, err_msg=f"{name} step {s}")
+        if m is not None:
+            np.testing.assert_allclose(m, d["adagrad_state"], rtol=1e-5, atol=1e-7)
