@@ -20,6 +20,8 @@ struct pb200_host_ctx {
 
 using namespace pb200;
 
+extern "C" int pb200_host_ctx_destroy(pb200_host_ctx *c);
+
 extern "C" int pb200_host_ctx_create(pb200_host_ctx **ctx, int64_t max_indices_per_group,
                                      int64_t max_bags_per_group, int32_t dim) {
     if (!ctx || max_indices_per_group < 1 || max_bags_per_group < 1 || dim < 1) return PB200_EINVAL;
@@ -28,18 +30,27 @@ extern "C" int pb200_host_ctx_create(pb200_host_ctx **ctx, int64_t max_indices_p
     c->max_idx = max_indices_per_group;
     c->max_bags = max_bags_per_group;
     c->dim = dim;
-    for (int i = 0; i < 2; ++i) {
-        PB200_CUDA_TRY(cudaMalloc(&c->d_idx[i], (size_t)(c->max_idx + 4) * 8));
-        PB200_CUDA_TRY(cudaMalloc(&c->d_off[i], (size_t)(c->max_bags + 4) * 8));
-        PB200_CUDA_TRY(cudaMalloc(&c->d_out[i], (size_t)c->max_bags * dim * 4));
-        PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
-        PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
-        PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
-        PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bwd[i], cudaEventDisableTiming));
+    // any failure below releases what was created so far (calloc zeroed every handle)
+    auto create = [&]() -> int {
+        for (int i = 0; i < 2; ++i) {
+            PB200_CUDA_TRY(cudaMalloc(&c->d_idx[i], (size_t)(c->max_idx + 4) * 8));
+            PB200_CUDA_TRY(cudaMalloc(&c->d_off[i], (size_t)(c->max_bags + 4) * 8));
+            PB200_CUDA_TRY(cudaMalloc(&c->d_out[i], (size_t)c->max_bags * dim * 4));
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+            PB200_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bwd[i], cudaEventDisableTiming));
+        }
+        PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+        PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        return PB200_OK;
+    };
+    const int rc = create();
+    if (rc != PB200_OK) {
+        pb200_host_ctx_destroy(c);
+        return rc;
     }
-    PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-    PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
-    PB200_CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     *ctx = c;
     return PB200_OK;
 }
