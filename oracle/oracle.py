@@ -211,15 +211,18 @@ def fused_optimizer_step(weights, grad, optimizer="exact_sgd", lr=0.01, eps=1.0e
     Rows outside `touched` (bool [rows]; default: rows with a non-zero gradient are irrelevant because
     an all-zero gradient leaves both w and m unchanged) are left alone.
     Returns (new_weights float64, new_state float64 or None)."""
-    w = np.asarray(weights, dtype=np.float64).copy()
-    g = np.asarray(grad, dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64).copy()
+    g = np.ascontiguousarray(grad, dtype=np.float64)
     if touched is not None:
-        g = g * np.asarray(touched, dtype=np.float64)[:, None]
+        g = np.ascontiguousarray(g * np.asarray(touched, dtype=np.float64)[:, None])
     if optimizer in ("sgd", "exact_sgd"):
-        return w - lr * g, None
-    if optimizer in ("rowwise_adagrad", "exact_row_wise_adagrad", "exact_rowwise_adagrad"):
-        m = np.zeros(w.shape[0]) if state is None else np.asarray(state, dtype=np.float64).copy()
-        m = m + (g * g).mean(axis=1)
-        mult = lr / (np.sqrt(m) + eps)
-        return w - mult[:, None] * g, m
-    raise ValueError(f"unknown optimizer {optimizer}")
+        code, m = 1, None
+    elif optimizer in ("rowwise_adagrad", "exact_row_wise_adagrad", "exact_rowwise_adagrad"):
+        code = 2
+        m = np.zeros(w.shape[0]) if state is None else np.ascontiguousarray(state, dtype=np.float64).copy()
+    else:
+        raise ValueError(f"unknown optimizer {optimizer}")
+    _load().oracle_fused_optimizer_step(_p(w, C.c_double), _p(m, C.c_double), _p(g, C.c_double),
+                                        C.c_int64(w.shape[0]), C.c_int32(w.shape[1]), C.c_int32(code),
+                                        C.c_double(lr), C.c_double(eps))
+    return w, m

@@ -257,3 +257,33 @@ void oracle_calculate_lengths(const int64_t *offsets, int64_t n_bags, int64_t n_
     for (int64_t i = 0; i < n_bags; ++i)
         lengths[i] = (i + 1 < n_bags ? offsets[i + 1] : n_indices) - offsets[i];
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused "exact" optimizers of the batched op the reference builds for its emb_lookup kernel
+ * (train/comms/pt/comms_utils.py:2015 optimizer=OptimType.EXACT_ROWWISE_ADAGRAD;
+ * train/compute/python/workloads/pytorch/split_table_batched_embeddings_ops.py:279-301 lr / eps).
+ * fbgemm_gpu itself is not in the reference tree: this restates its published update — `grad` is
+ * the dense-equivalent gradient of ONE step (oracle_tbe_bwd), every row gets one update:
+ *   optimizer 1 (exact_sgd)              w -= lr * g
+ *   optimizer 2 (exact_row_wise_adagrad) m[row] += mean_d(g[row,d]^2);
+ *                                        w[row] -= lr / (sqrt(m[row]) + eps) * g[row]
+ * float64 throughout.  Pinned against torch.optim.SGD / torch.optim.Adagrad on row-constant
+ * gradients (tests/test_oracle_golden.py, tests/golden/tbe_optim_torch.npz).
+ * ------------------------------------------------------------------------------------------- */
+#include <math.h>
+
+void oracle_fused_optimizer_step(double *weights, double *state, const double *grad, int64_t rows,
+                                 int32_t dim, int32_t optimizer, double lr, double eps) {
+    for (int64_t r = 0; r < rows; ++r) {
+        const double *g = grad + r * dim;
+        double *w = weights + r * dim;
+        double mult = lr;
+        if (optimizer == 2) {
+            double ss = 0.0;
+            for (int32_t d = 0; d < dim; ++d) ss += g[d] * g[d];
+            state[r] += ss / (double)dim;
+            mult = lr / (sqrt(state[r]) + eps);
+        }
+        for (int32_t d = 0; d < dim; ++d) w[d] -= mult * g[d];
+    }
+}
