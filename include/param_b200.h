@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 1
+#define PB200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define PB200_OK 0
@@ -168,6 +168,15 @@ int pb200_check_indices(const int64_t *table_row_offsets, int32_t num_tables,
  * PB200_BWD_SORTED / PB200_BWD_EXACT need scratch: query the size with
  * pb200_tbe_bwd_scratch_bytes() and pass a device buffer of that size.
  * PB200_BWD_EXACT is pb200_tbe_bwd_fused (section 3b) with SGD, lr = -scale, fp32 rows.
+ *
+ * max_table_rows: an upper bound of the row count of the largest table (host value; the caller
+ *   built table_row_offsets, so it knows).  It fixes the number of radix passes of the sort
+ *   (20 key bits for 1 M rows = two 10-bit passes); <= 0 = unknown, the sort then covers all 32
+ *   bits of a row id.  Nothing is read back from the device: the call never synchronises and is
+ *   CUDA-graph capturable.
+ * plan_ready != 0: `scratch` already holds the sort plan that pb200_tbe_plan_build (section 3c)
+ *   produced for exactly these indices / offsets / psw / pool_mode / gradient strides; the call
+ *   then launches the segmented reduce only.
  */
 int64_t pb200_tbe_bwd_scratch_bytes(int64_t n_indices, int32_t num_tables, int64_t batch,
                                     int64_t total_rows, int32_t algo);
@@ -176,8 +185,8 @@ int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32_t num_tabl
                   const void *offsets, int64_t batch, int32_t idx_type,
                   const float *psw, int32_t pool_mode,
                   const float *grad_out, int64_t go_stride_t, int64_t go_stride_b,
-                  float scale, int32_t algo,
-                  void *scratch, int64_t scratch_bytes, void *stream);
+                  float scale, int32_t algo, int64_t max_table_rows,
+                  void *scratch, int64_t scratch_bytes, int32_t plan_ready, void *stream);
 
 /* =========================================================================
  * 3b. Backward with the optimizer fused in ("exact": one update per touched row)
@@ -202,8 +211,10 @@ int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32_t num_tabl
  * stochastically with a counter-based generator keyed on (sr_seed, element) — pass a new
  * sr_seed per step; 0 = round to nearest even.
  * scratch: pb200_tbe_bwd_fused_scratch_bytes() bytes of device memory.
+ * max_table_rows, plan_ready: as for pb200_tbe_bwd.
  */
-int64_t pb200_tbe_bwd_fused_scratch_bytes(int64_t n_indices, int32_t num_tables, int32_t dim);
+int64_t pb200_tbe_bwd_fused_scratch_bytes(int64_t n_indices, int32_t num_tables, int64_t batch,
+                                          int32_t dim);
 int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *state,
                         const int64_t *table_row_offsets, int32_t num_tables, int32_t dim,
                         const void *indices, int64_t n_indices,
@@ -211,8 +222,34 @@ int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *state,
                         const float *psw, int32_t pool_mode,
                         const float *grad_out, int64_t go_stride_t, int64_t go_stride_b,
                         int32_t optimizer, float lr, float eps,
-                        int32_t stochastic_rounding, uint64_t sr_seed,
-                        void *scratch, int64_t scratch_bytes, void *stream);
+                        int32_t stochastic_rounding, uint64_t sr_seed, int64_t max_table_rows,
+                        void *scratch, int64_t scratch_bytes, int32_t plan_ready, void *stream);
+
+/* =========================================================================
+ * 3c. Sort plan: the index-only half of the sort-based backward, ahead of the gradient
+ * =========================================================================
+ * Replaces: the radix sort + index bookkeeping inside the autograd backward of
+ *   nn.EmbeddingBag / fbgemm TBE (train/comms/pt/pytorch_dist_backend.py:849-857,
+ *   dlrm.py:1296), which the reference can only start once the gradient has arrived.
+ *
+ * The sort of the lookups by row depends on indices / offsets only.  This call builds it into
+ * `scratch` (same buffer and size as the backward call that will consume it, SORTED or EXACT)
+ * on `stream` — typically a side stream, while the forward lookup of the same request runs —
+ * and the backward is then called with plan_ready = 1 and launches the segmented reduce alone.
+ * Hand-written per-table LSD radix sort (param_b200/csrc/radix_sort.cu): the table is known from the
+ * position, so only the table-relative row is sorted (ceil(bits(max_table_rows) / 10) passes);
+ * the first pass reads the indices and derives the gradient-row offset of each lookup from the
+ * offsets, the last pass emits arena rows: one globally sorted array.  Stable: equal rows keep
+ * request order, so the reducers' summation order is fixed.  psw / pool_mode / go_stride_* must
+ * be the ones the backward call will use (they are folded into the plan's values).
+ */
+int pb200_tbe_plan_build(void *scratch, int64_t scratch_bytes,
+                         const int64_t *table_row_offsets, int64_t max_table_rows,
+                         int32_t num_tables, int32_t dim,
+                         const void *indices, int64_t n_indices,
+                         const void *offsets, int64_t batch, int32_t idx_type,
+                         const float *psw, int32_t pool_mode,
+                         int64_t go_stride_t, int64_t go_stride_b, void *stream);
 
 /* =========================================================================
  * 4. Peer-memory all-to-all (single node, NVLink 5 / NVSwitch)

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "pb200_abi_version", "pb200_error_string", "pb200_launch_count", "pb200_device_info",
     "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_tbe_fwd_f16", "pb200_check_indices",
     "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd",
-    "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused",
+    "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused", "pb200_tbe_plan_build",
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
     "pb200_a2a_comm_error", "pb200_a2a_single",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_tbe_fwd_a2a",
@@ -93,10 +93,12 @@ def load():
     sig("pb200_check_indices", C.c_int, vp, i32, vp, i64, vp, i64, i32, vp, vp)
     sig("pb200_tbe_bwd_scratch_bytes", i64, i64, i32, i64, i64, i32)
     sig("pb200_tbe_bwd", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64,
-        f32, i32, vp, i64, vp)
-    sig("pb200_tbe_bwd_fused_scratch_bytes", i64, i64, i32, i32)
+        f32, i32, i64, vp, i64, i32, vp)
+    sig("pb200_tbe_bwd_fused_scratch_bytes", i64, i64, i32, i64, i32)
     sig("pb200_tbe_bwd_fused", C.c_int, vp, i32, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp,
-        i64, i64, i32, f32, f32, i32, u64, vp, i64, vp)
+        i64, i64, i32, f32, f32, i32, u64, i64, vp, i64, i32, vp)
+    sig("pb200_tbe_plan_build", C.c_int, vp, i64, vp, i64, i32, i32, vp, i64, vp, i64, i32, vp, i32,
+        i64, i64, vp)
     sig("pb200_a2a_comm_create", C.c_int, C.POINTER(vp), i32, i32, C.POINTER(vp), C.POINTER(vp), i64)
     sig("pb200_a2a_comm_destroy", C.c_int, vp)
     sig("pb200_a2a_comm_config", C.c_int, vp, i32, C.c_double)
@@ -116,7 +118,7 @@ def load():
         i32, f32)
     sig("pb200_fill_uniform", C.c_int, vp, i64, f32, f32, u64, vp)
     sig("pb200_fill_zipf_indices", C.c_int, vp, i64, i32, vp, i64, i32, u64, vp)
-    if lib.pb200_abi_version() != 1:
+    if lib.pb200_abi_version() != 2:
         raise PB200Error("libparam_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -176,6 +176,12 @@ class DLRMParallelEmbedding:
                           torch.empty(n_len + 1, dtype=torch.int64, device=device),
                           torch.empty(self.cap_indices, dtype=torch.int64, device=device))
         self.device_side_dist = True
+        # the backward's sort needs the indices only: it is queued on a side stream at forward time
+        # (ops.tbe_plan) and the backward after the gradient exchange is the segmented reduce alone
+        self.presort = bwd_algo in ("sorted", "exact", "auto")
+        self._side = torch.cuda.Stream(device=device) if self.presort else None
+        self._plan, self._plan_buf = None, None
+        self.max_table_rows = max(rows) if rows else 0
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------
     def sparse_data_dist(self, batch: SparseBatch, device_side: Optional[bool] = None):
@@ -218,6 +224,12 @@ class DLRMParallelEmbedding:
         ONE kernel whose epilogue stores pooled rows into the peers' windows (pb200_tbe_fwd_a2a);
         fused=False: lookup kernel to a local [N, T_l*E] buffer, then the push kernel."""
         self._saved = (offsets, indices)
+        self._plan = None
+        if self.presort:
+            self._plan = ops.tbe_plan(self.arena.row_offsets, self.T_local, self.E, indices, offsets, self.N,
+                                      self.max_table_rows, layout="BTD", exact=self.bwd_algo == "exact",
+                                      stream=self._side, buf=self._plan_buf)
+            self._plan_buf = self._plan.buf
         if self.fused if fused is None else fused:
             return self.window.lookup_forward_fused(self.arena, indices, offsets, self.batch_split,
                                                     self.tables_split, out_window_off=self.off_pooled)
@@ -231,7 +243,8 @@ class DLRMParallelEmbedding:
         g_local = self.window.pooled_backward(grad.contiguous(), self.batch_split, self.tables_split,
                                               self.E, out_window_off=self.off_grad)
         ops.tbe_backward(self.arena.weights, self.arena.row_offsets, self.T_local, self.E, indices,
-                         offsets, self.N, g_local, layout="BTD", scale=-self.lr, algo=self.bwd_algo)
+                         offsets, self.N, g_local, layout="BTD", scale=-self.lr, algo=self.bwd_algo,
+                         max_table_rows=self.max_table_rows, plan=self._plan)
 
 
 class NCCLReferenceEmbedding:

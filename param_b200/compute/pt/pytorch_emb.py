@@ -62,7 +62,7 @@ class B200EmbeddingBag(nn.Module):
     def __init__(self, num_embeddings: int, embedding_dim: int, mode: str = "sum",
                  sparse: bool = False, include_last_offset: bool = False,
                  _weight: Optional[torch.Tensor] = None, device=None,
-                 fwd_algo: str = "auto", bwd_algo: str = "atomic") -> None:
+                 fwd_algo: str = "auto", bwd_algo: str = "auto") -> None:
         super().__init__()
         if mode not in ("sum", "mean"):
             raise PB200Error(f"mode {mode!r} is not on the PARAM hot path (sum/mean only)")

@@ -34,11 +34,23 @@ class _TBEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, op, indices, offsets, psw):
         B = (offsets.numel() - 1) // op.arena.num_tables
+        if psw is not None:      # one fp32 copy shared by the lookup, the sort plan and the backward
+            psw = psw.contiguous().view(-1).float()
+        indices, offsets = indices.contiguous().view(-1), offsets.contiguous().view(-1)
         out = ops.tbe_forward(op.arena, indices, offsets, B, mode=op.pooling_mode,
                               per_sample_weights=psw, layout="BTD", algo=op.fwd_algo)
         ctx.op, ctx.B = op, B
         ctx.save_for_backward(indices, offsets, psw if psw is not None else torch.empty(0))
         ctx.weighted = psw is not None
+        ctx.plan = None
+        if op.presort and op.bwd_algo != "atomic" and ctx.needs_input_grad[0] and indices.numel() >= 65536:
+            # the sort of the backward depends on the request only: queue it beside the lookup
+            if op._side is None:
+                op._side = torch.cuda.Stream(device=out.device)
+            ctx.plan = ops.tbe_plan(op.arena.row_offsets, op.arena.num_tables, op.arena.dim,
+                                    indices, offsets, B, op.max_table_rows, layout="BTD", mode=op.pooling_mode,
+                                    per_sample_weights=psw,
+                                    exact=op.bwd_algo == "exact", stream=op._side)
         return out
 
     @staticmethod
@@ -49,7 +61,8 @@ class _TBEFn(torch.autograd.Function):
         if op.bwd_algo in ("sorted", "atomic"):
             ops.tbe_backward(op.arena.weights, op.arena.row_offsets, op.arena.num_tables, op.arena.dim,
                              indices, offsets, ctx.B, grad.contiguous(), layout="BTD", scale=-op.lr,
-                             mode=op.pooling_mode, per_sample_weights=psw, algo=op.bwd_algo)
+                             mode=op.pooling_mode, per_sample_weights=psw, algo=op.bwd_algo,
+                             max_table_rows=op.max_table_rows, plan=ctx.plan)
         else:
             op.step += 1
             ops.tbe_backward_fused(op.arena.weights, op.arena.row_offsets, op.arena.num_tables,
@@ -57,7 +70,8 @@ class _TBEFn(torch.autograd.Function):
                                    optimizer=op.optimizer, lr=op.lr, eps=op.eps, state=op.momentum1,
                                    layout="BTD", mode=op.pooling_mode, per_sample_weights=psw,
                                    stochastic_rounding=op.stochastic_rounding,
-                                   sr_seed=op.seed * 0x9E3779B1 + op.step)
+                                   sr_seed=op.seed * 0x9E3779B1 + op.step,
+                                   max_table_rows=op.max_table_rows, plan=ctx.plan)
         return None, None, None, None, None
 
 
@@ -106,6 +120,9 @@ class B200TBE(nn.Module):
         self.stochastic_rounding = bool(stochastic_rounding) and dtype == torch.float16
         self.seed, self.step = int(seed), 0
         self.fwd_algo, self.bwd_algo = fwd_algo, bwd_algo
+        self.max_table_rows = max(r for r, _ in self.embedding_specs)
+        # presort: build the backward's sort plan on a side stream during the forward (large requests)
+        self.presort, self._side = True, None
         # autograd needs one differentiable input to route the backward through
         self._anchor = nn.Parameter(torch.zeros(1, device=device))
 

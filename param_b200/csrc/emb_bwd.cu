@@ -9,9 +9,11 @@
 //
 // ATOMIC : one lane group per bag; the bag's gradient row is read once (16 B per lane) and
 //          red.global.add.v4.f32 is issued per lookup.  Summation order across bags is not fixed.
-// SORTED : per chunk of tables — (1) build (arena row, bag) pairs, (2) cub radix sort by row,
-//          (3) one lane group per 256 sorted entries accumulates runs of equal rows in registers and
-//          issues ONE red per (segment, row).  Under Zipf skew ~87 % of the lookups of a table-batch
+// SORTED : (1) the sort plan — every table's lookups sorted by row, a hand-written radix sort fused with
+//          the pair build (radix_sort.cu); it needs the indices only, so the host layer builds it on a
+//          side stream at forward time (pb200_tbe_plan_build) — and (2) ONE segmented-reduce launch: a
+//          lane group per 256 sorted entries accumulates runs of equal rows in registers and issues ONE
+//          red per (segment, row).  Under Zipf skew ~87 % of the lookups of a table-batch
 //          are duplicates, so the number of L2 read-modify-writes drops ~8x and hot rows no longer
 //          serialise on one L2 slice; rows wholly inside a segment are updated exactly once
 //          (deterministic), only runs crossing a segment boundary are combined by a few reds.
@@ -140,6 +142,7 @@ __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long lon
     const int lane_g = lane & (G - 1);
     const int grp = lane / G;
     const int vec4 = p.dim >> 2;
+    n = min(n, *p.n_dev);    // n is the host's capacity, the plan knows the count
     const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
     const long long s0 = seg * seg_len;
     const long long s1 = min(s0 + (long long)seg_len, n);
@@ -274,60 +277,93 @@ using namespace pb200;
 
 extern "C" int64_t pb200_tbe_bwd_scratch_bytes(int64_t n_indices, int32_t num_tables, int64_t batch,
                                                int64_t total_rows, int32_t algo) {
-    (void)batch;
     (void)total_rows;
     if (algo == PB200_BWD_EXACT)   // dim is not known here: size for the widest supported row
-        return pb200_tbe_bwd_fused_scratch_bytes(n_indices, num_tables, 512);
+        return pb200_tbe_bwd_fused_scratch_bytes(n_indices, num_tables, batch, 512);
     if (algo != PB200_BWD_SORTED && algo != PB200_BWD_AUTO) return 0;
-    if (n_indices <= 0) return 0;
-    SortedPlan pl = plan_sorted(n_indices, num_tables, true);
-    return (int64_t)sorted_scratch_need(pl, num_tables);
+    if (n_indices <= 0 || num_tables < 1 || batch < 1) return 0;
+    return (int64_t)plan_layout(n_indices, num_tables, batch, 0, seg_len_from_env()).total;
+}
+
+extern "C" int pb200_tbe_plan_build(void *scratch, int64_t scratch_bytes,
+                                    const int64_t *table_row_offsets, int64_t max_table_rows,
+                                    int32_t num_tables, int32_t dim, const void *indices,
+                                    int64_t n_indices, const void *offsets, int64_t batch,
+                                    int32_t idx_type, const float *psw, int32_t pool_mode,
+                                    int64_t go_stride_t, int64_t go_stride_b, void *stream) {
+    if (!table_row_offsets || !offsets || (!indices && n_indices > 0)) return PB200_EINVAL;
+    if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
+    if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
+    if (idx_type != PB200_IDX_I64 && idx_type != PB200_IDX_I32) return PB200_EINVAL;
+    if (batch == 0 || n_indices == 0) return PB200_OK;
+    if (go_stride_t % 4 != 0 || go_stride_b % 4 != 0) return PB200_EALIGN;
+    // the sort part of the layout is the same for SORTED and EXACT (reducer extras sit behind it)
+    const PlanLayout L = plan_layout(n_indices, num_tables, batch, 0, seg_len_from_env());
+    if (!scratch || scratch_bytes < (int64_t)L.total) return PB200_EINVAL;
+    BwdParams p{};
+    p.table_row_offsets = (const long long *)table_row_offsets;
+    p.indices = indices;
+    p.offsets = offsets;
+    p.psw = psw;
+    p.n_indices = n_indices;
+    p.batch = batch;
+    p.n_bags = (long long)num_tables * batch;
+    p.go_stride_t = go_stride_t;
+    p.go_stride_b = go_stride_b;
+    p.num_tables = num_tables;
+    p.dim = dim;
+    p.mean = pool_mode == PB200_POOL_MEAN;
+    return build_sort_plan(p, idx_type, max_table_rows, scratch, L, (cudaStream_t)stream);
 }
 
 namespace pb200 {
 
-template <typename index_t>
-static int bwd_sorted(const BwdParams &p, void *scratch, long long scratch_bytes, cudaStream_t st) {
+static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows, void *scratch,
+                      long long scratch_bytes, bool plan_ready, cudaStream_t st) {
     const bool side = (p.psw != nullptr) || p.mean;
     const int seg_len = seg_len_from_env();
     static const int seg_occ4 = [] {
         const char *e = getenv("PB200_SEG_OCC4");
         return e ? atoi(e) : 0;
     }();
-    const SortedPlan pl = plan_sorted(p.n_indices, p.num_tables, true);
+    const PlanLayout L = plan_layout(p.n_indices, p.num_tables, p.batch, 0, seg_len);
+    if (!scratch || scratch_bytes < (long long)L.total) return PB200_EINVAL;
+    if (p.n_indices > 0x7fffffffll) return PB200_EUNSUPPORTED;
+    if (!plan_ready) {
+        const int rc = build_sort_plan(p, idx_type, max_table_rows, scratch, L, st);
+        if (rc != PB200_OK) return rc;
+    }
+    const SortedView v = sorted_view(scratch, L, p.n_indices);
+    BwdParams pr = p;
+    pr.n_dev = v.count;
     const int vec4 = p.dim >> 2;
-
-    // segmented reduce of one sorted chunk
-    auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
-        const long long n = c.n, row0 = c.row0;
-        const unsigned *ks = c.ks, *vs = c.vs;
-        const long long n_seg = (n + seg_len - 1) / seg_len;
+    const long long n = v.n, n_seg = v.n_seg;
+    // segmented reduce of the whole request: ONE launch (the keys are arena rows, globally sorted)
 #define PB200_SEG_LAUNCH(G_, C_)                                                                \
     do {                                                                                        \
         const long long per_block = 8ll * (32 / G_);                                            \
         const long long g2 = (n_seg + per_block - 1) / per_block;                               \
+        if (g2 > 0x7fffffffll) return PB200_EUNSUPPORTED;                                       \
         if (side)                                                                               \
-            segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, s>>>(                   \
-                p, n, row0, ks, vs, ss.goff_of, ss.w_of, seg_len);                              \
+            segment_reduce_kernel<G_, C_, true><<<(unsigned)g2, 256, 0, st>>>(                  \
+                pr, n, 0, v.keys, v.vals, v.goff_of, v.w_of, seg_len);                           \
         else if (seg_occ4)                                                                      \
-            segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, s>>>(             \
-                p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
+            segment_reduce_kernel_occ4<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(            \
+                pr, n, 0, v.keys, v.vals, nullptr, nullptr, seg_len);                            \
         else                                                                                    \
-            segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, s>>>(                  \
-                p, n, row0, ks, vs, nullptr, nullptr, seg_len);                                 \
+            segment_reduce_kernel<G_, C_, false><<<(unsigned)g2, 256, 0, st>>>(                 \
+                pr, n, 0, v.keys, v.vals, nullptr, nullptr, seg_len);                            \
     } while (0)
-        if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
-        else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);
-        else if (vec4 <= 16) PB200_SEG_LAUNCH(16, 1);
-        else if (vec4 <= 32) PB200_SEG_LAUNCH(32, 1);
-        else if (vec4 <= 64) PB200_SEG_LAUNCH(32, 2);
-        else PB200_SEG_LAUNCH(32, 4);
+    if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
+    else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);
+    else if (vec4 <= 16) PB200_SEG_LAUNCH(16, 1);
+    else if (vec4 <= 32) PB200_SEG_LAUNCH(32, 1);
+    else if (vec4 <= 64) PB200_SEG_LAUNCH(32, 2);
+    else PB200_SEG_LAUNCH(32, 4);
 #undef PB200_SEG_LAUNCH
-        count_launch();
-        PB200_LAUNCH_CHECK();
-        return PB200_OK;
-    };
-    return bwd_sorted_pipeline<index_t>(p, pl, scratch, scratch_bytes, st, /*full_key=*/false, reduce);
+    count_launch();
+    PB200_LAUNCH_CHECK();
+    return PB200_OK;
 }
 
 template <typename index_t, int G, int C>
@@ -346,8 +382,8 @@ static int launch_atomic(const BwdParams &p, cudaStream_t st) {
 }
 
 template <typename index_t>
-static int dispatch_bwd(const BwdParams &p, int algo, void *scratch, long long scratch_bytes,
-                        cudaStream_t st) {
+static int dispatch_bwd(const BwdParams &p, int algo, int idx_type, long long max_table_rows,
+                        void *scratch, long long scratch_bytes, bool plan_ready, cudaStream_t st) {
     if (p.n_bags == 0 || p.n_indices == 0) return PB200_OK;
     const bool vec_ok = (p.dim % 4 == 0) && (p.dim <= 512) && (((uintptr_t)p.dst & 15) == 0) &&
                         (((uintptr_t)p.grad_out & 15) == 0) && (p.go_stride_t % 4 == 0) &&
@@ -361,7 +397,8 @@ static int dispatch_bwd(const BwdParams &p, int algo, void *scratch, long long s
         return PB200_OK;
     }
     if (algo == PB200_BWD_AUTO) algo = scratch ? PB200_BWD_SORTED : PB200_BWD_ATOMIC;
-    if (algo == PB200_BWD_SORTED) return bwd_sorted<index_t>(p, scratch, scratch_bytes, st);
+    if (algo == PB200_BWD_SORTED)
+        return bwd_sorted(p, idx_type, max_table_rows, scratch, scratch_bytes, plan_ready, st);
     const int vec4 = p.dim >> 2;
     if (vec4 <= 4) return launch_atomic<index_t, 4, 1>(p, st);
     if (vec4 <= 8) return launch_atomic<index_t, 8, 1>(p, st);
@@ -377,18 +414,19 @@ extern "C" int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32
                              int32_t dim, const void *indices, int64_t n_indices,
                              const void *offsets, int64_t batch, int32_t idx_type, const float *psw,
                              int32_t pool_mode, const float *grad_out, int64_t go_stride_t,
-                             int64_t go_stride_b, float scale, int32_t algo, void *scratch,
-                             int64_t scratch_bytes, void *stream) {
+                             int64_t go_stride_b, float scale, int32_t algo, int64_t max_table_rows,
+                             void *scratch, int64_t scratch_bytes, int32_t plan_ready, void *stream) {
     if (!dst || !table_row_offsets || !offsets || !grad_out || (!indices && n_indices > 0))
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
     if (algo < PB200_BWD_AUTO || algo > PB200_BWD_EXACT) return PB200_EINVAL;
+    if (plan_ready && (!scratch || algo == PB200_BWD_ATOMIC)) return PB200_EINVAL;
     if (algo == PB200_BWD_EXACT)   // dst -= (-scale) * dW with every touched row written exactly once
         return pb200_tbe_bwd_fused(dst, PB200_W_F32, nullptr, table_row_offsets, num_tables, dim,
                                    indices, n_indices, offsets, batch, idx_type, psw, pool_mode,
                                    grad_out, go_stride_t, go_stride_b, PB200_OPT_SGD, -scale, 0.f, 0,
-                                   0, scratch, scratch_bytes, stream);
+                                   0, max_table_rows, scratch, scratch_bytes, plan_ready, stream);
     BwdParams p{};
     p.dst = dst;
     p.table_row_offsets = (const long long *)table_row_offsets;
@@ -406,7 +444,10 @@ extern "C" int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32
     p.dim = dim;
     p.mean = pool_mode == PB200_POOL_MEAN;
     cudaStream_t st = (cudaStream_t)stream;
-    if (idx_type == PB200_IDX_I64) return dispatch_bwd<long long>(p, algo, scratch, scratch_bytes, st);
-    if (idx_type == PB200_IDX_I32) return dispatch_bwd<int>(p, algo, scratch, scratch_bytes, st);
+    const bool ready = plan_ready != 0;
+    if (idx_type == PB200_IDX_I64)
+        return dispatch_bwd<long long>(p, algo, idx_type, max_table_rows, scratch, scratch_bytes, ready, st);
+    if (idx_type == PB200_IDX_I32)
+        return dispatch_bwd<int>(p, algo, idx_type, max_table_rows, scratch, scratch_bytes, ready, st);
     return PB200_EINVAL;
 }

@@ -14,8 +14,8 @@
 // w -= lr / (sqrt(m) + eps) * g.  Parity for this op is unpinned)
 //
 // A non-linear update needs the COMPLETE gradient of a row, so the "one red per (segment, row)" of
-// the SORTED variant (emb_bwd.cu) is not enough.  Per chunk of tables, after the same pair build +
-// radix sort (emb_bwd_common.cuh):
+// the SORTED variant (emb_bwd.cu) is not enough.  Over the same sort plan (sort_plan.cuh, radix_sort.cu — all
+// lookups of the request sorted by arena row), one launch each:
 //   E1 exact_reduce_kernel   one lane group per 256 sorted entries, runs of equal rows summed in
 //                            registers.  A run that lies wholly inside the segment is final: the
 //                            optimizer is applied on the spot (row read once, written once).  The
@@ -180,6 +180,7 @@ __device__ __forceinline__ void exact_reduce_body(const BwdParams &p, const OptP
     const int grp = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int vec4 = p.dim >> 2;
+    n = min(n, *p.n_dev);    // n is the host's capacity, the plan knows the count
     const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
     const long long s0 = seg * seg_len;
     const long long s1 = min(s0 + (long long)seg_len, n);
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(256) exact_boundary_kernel(const BwdParams p, 
     const int grp = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int vec4 = p.dim >> 2;
+    n = min(n, *p.n_dev);
     const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
     const long long s0 = seg * seg_len;
     if (s0 >= n) return;
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(256) exact_long_run_kernel(const BwdParams p, 
 #pragma unroll
     for (int c = 0; c < C; ++c) col_ok[c] = c * G + lane_g < vec4;
     const unsigned count = *work_count;
+    n = min(n, *p.n_dev);
     for (unsigned item = blockIdx.x; item < count; item += gridDim.x) {
         const long long seg = worklist[item];
         const long long s1 = min((seg + 1) * (long long)seg_len, n);
@@ -561,19 +564,26 @@ __global__ void __launch_bounds__(256) exact_long_run_kernel(const BwdParams p, 
     }
 }
 
-constexpr long long kExactPairCap = 32ll << 20;   // keeps the partial-sum buffer at <= 256 MB per set (dim 128)
-
-static SortedPlan plan_exact(long long n_indices, int num_tables, int dim, int seg_len) {
-    // per segment: head + tail partial sums ([2][dim] fp32) and 8 bytes of work-list space
-    return plan_sorted(n_indices, num_tables, true, kExactPairCap, (size_t)2 * (size_t)dim * 4 + 8, seg_len);
+// per segment: head + tail partial sums ([2][dim] fp32) and 8 bytes of work-list space
+static PlanLayout plan_exact(long long n_indices, int num_tables, long long batch, int dim, int seg_len) {
+    return plan_layout(n_indices, num_tables, batch, (size_t)2 * (size_t)dim * 4 + 8, seg_len);
 }
 
-template <typename index_t, typename WT>
-static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, long long scratch_bytes,
-                     cudaStream_t st) {
+template <typename WT>
+static int bwd_exact(const BwdParams &p, const OptParams &op, int idx_type, long long max_table_rows,
+                     void *scratch, long long scratch_bytes, bool plan_ready, cudaStream_t s) {
     const bool side = (p.psw != nullptr) || p.mean;
     const int seg_len = seg_len_from_env();
-    const SortedPlan pl = plan_exact(p.n_indices, p.num_tables, p.dim, seg_len);
+    const PlanLayout L = plan_exact(p.n_indices, p.num_tables, p.batch, p.dim, seg_len);
+    if (!scratch || scratch_bytes < (long long)L.total) return PB200_EINVAL;
+    if (p.n_indices > 0x7fffffffll) return PB200_EUNSUPPORTED;
+    if (!plan_ready) {
+        const int rc = build_sort_plan(p, idx_type, max_table_rows, scratch, L, s);
+        if (rc != PB200_OK) return rc;
+    }
+    const SortedView sv = sorted_view(scratch, L, p.n_indices);
+    BwdParams pr = p;
+    pr.n_dev = sv.count;
     const int vec4 = p.dim >> 2;
     const bool adagrad = op.optimizer == PB200_OPT_ROWWISE_ADAGRAD;
     // measured (profiles/r01f): 3 resident CTAs/SM speed the Adagrad / fp16 variants up by 6-13 %
@@ -581,60 +591,56 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
         const char *e = getenv("PB200_EXACT_OCC3");
         return e ? atoi(e) : 1;
     }();
-    const long long n_seg_cap = (pl.max_pairs + seg_len - 1) / seg_len;
-
-    auto reduce = [&](const SortedChunk &c, const SortSet &ss, cudaStream_t s) -> int {
-        const long long n = c.n, row0 = c.row0;
-        const unsigned *ks = c.ks, *vs = c.vs;
-        float4 *partial = (float4 *)ss.extra;
-        const long long n_seg = (n + seg_len - 1) / seg_len;
-        // behind the partial sums: the long-run work list (one entry per segment at most) + its counter
-        unsigned *worklist = (unsigned *)(ss.extra + (size_t)n_seg_cap * 2 * (size_t)p.dim * 4);
-        unsigned *work_count = worklist + n_seg_cap;
-        if (n_seg > 1) PB200_CUDA_TRY(cudaMemsetAsync(work_count, 0, 4, s));
-        long long g3 = 4ll * sm_count();
-        if (g3 > n_seg) g3 = n_seg;
+    // ONE reduce over the whole request: the keys are arena rows, sorted over all tables
+    const long long n = sv.n, row0 = 0, n_seg = sv.n_seg;
+    const unsigned *ks = sv.keys, *vs = sv.vals;
+    float4 *partial = (float4 *)sv.extra;
+    // behind the partial sums: the long-run work list (one entry per segment at most) + its counter
+    unsigned *worklist = (unsigned *)(sv.extra + (size_t)n_seg * 2 * (size_t)p.dim * 4);
+    unsigned *work_count = worklist + n_seg;
+    if (n_seg > 1) PB200_CUDA_TRY(cudaMemsetAsync(work_count, 0, 4, s));
+    long long g3 = 4ll * sm_count();
+    if (g3 > n_seg) g3 = n_seg;
 #define PB200_EXACT_LAUNCH(G_, C_)                                                                 \
     do {                                                                                           \
         const long long per_block = 8ll * (32 / G_);                                               \
         const long long g2 = (n_seg + per_block - 1) / per_block;                                  \
+        if (g2 > 0x7fffffffll) return PB200_EUNSUPPORTED;                                          \
         if (!side && occ3 && G_ == 32 && C_ == 1 && adagrad)                                       \
             exact_reduce_kernel_occ3<WT, PB200_OPT_ROWWISE_ADAGRAD>                                \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, partial, seg_len);           \
         else if (!side && occ3 && G_ == 32 && C_ == 1)                                             \
             exact_reduce_kernel_occ3<WT, PB200_OPT_SGD>                                            \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, partial, seg_len);           \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, partial, seg_len);           \
         else if (side && adagrad)                                                                  \
             exact_reduce_kernel<WT, PB200_OPT_ROWWISE_ADAGRAD, G_, C_, true>                       \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, ss.goff_of, ss.w_of, partial, seg_len); \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, sv.goff_of, sv.w_of, partial, seg_len); \
         else if (side)                                                                             \
             exact_reduce_kernel<WT, PB200_OPT_SGD, G_, C_, true>                                   \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, ss.goff_of, ss.w_of, partial, seg_len); \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, sv.goff_of, sv.w_of, partial, seg_len); \
         else if (adagrad)                                                                          \
             exact_reduce_kernel<WT, PB200_OPT_ROWWISE_ADAGRAD, G_, C_, false>                      \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
         else                                                                                       \
             exact_reduce_kernel<WT, PB200_OPT_SGD, G_, C_, false>                                  \
-                <<<(unsigned)g2, 256, 0, s>>>(p, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
+                <<<(unsigned)g2, 256, 0, s>>>(pr, op, n, row0, ks, vs, nullptr, nullptr, partial, seg_len); \
         if (n_seg > 1) {                                                                           \
             exact_boundary_kernel<WT, G_, C_><<<(unsigned)g2, 256, 0, s>>>(                        \
-                p, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
+                pr, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
             exact_long_run_kernel<WT, G_, C_><<<(unsigned)g3, 256, 0, s>>>(                        \
-                p, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
+                pr, op, n, row0, ks, partial, worklist, work_count, seg_len);                       \
         }                                                                                          \
     } while (0)
-        if (vec4 <= 4) PB200_EXACT_LAUNCH(4, 1);
-        else if (vec4 <= 8) PB200_EXACT_LAUNCH(8, 1);
-        else if (vec4 <= 16) PB200_EXACT_LAUNCH(16, 1);
-        else if (vec4 <= 32) PB200_EXACT_LAUNCH(32, 1);
-        else if (vec4 <= 64) PB200_EXACT_LAUNCH(32, 2);
-        else PB200_EXACT_LAUNCH(32, 4);
+    if (vec4 <= 4) PB200_EXACT_LAUNCH(4, 1);
+    else if (vec4 <= 8) PB200_EXACT_LAUNCH(8, 1);
+    else if (vec4 <= 16) PB200_EXACT_LAUNCH(16, 1);
+    else if (vec4 <= 32) PB200_EXACT_LAUNCH(32, 1);
+    else if (vec4 <= 64) PB200_EXACT_LAUNCH(32, 2);
+    else PB200_EXACT_LAUNCH(32, 4);
 #undef PB200_EXACT_LAUNCH
-        count_launch(n_seg > 1 ? 3 : 1);
-        PB200_LAUNCH_CHECK();
-        return PB200_OK;
-    };
-    return bwd_sorted_pipeline<index_t>(p, pl, scratch, scratch_bytes, st, /*full_key=*/true, reduce);
+    count_launch(n_seg > 1 ? 3 : 1);
+    PB200_LAUNCH_CHECK();
+    return PB200_OK;
 }
 
 }  // namespace pb200
@@ -642,10 +648,9 @@ static int bwd_exact(const BwdParams &p, const OptParams &op, void *scratch, lon
 using namespace pb200;
 
 extern "C" int64_t pb200_tbe_bwd_fused_scratch_bytes(int64_t n_indices, int32_t num_tables,
-                                                     int32_t dim) {
-    if (n_indices <= 0 || num_tables < 1 || dim < 1) return 0;
-    const SortedPlan pl = plan_exact(n_indices, num_tables, dim, seg_len_from_env());
-    return (int64_t)sorted_scratch_need(pl, num_tables);
+                                                     int64_t batch, int32_t dim) {
+    if (n_indices <= 0 || num_tables < 1 || batch < 1 || dim < 1) return 0;
+    return (int64_t)plan_exact(n_indices, num_tables, batch, dim, seg_len_from_env()).total;
 }
 
 extern "C" int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *state,
@@ -654,8 +659,9 @@ extern "C" int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *s
                                    int64_t batch, int32_t idx_type, const float *psw,
                                    int32_t pool_mode, const float *grad_out, int64_t go_stride_t,
                                    int64_t go_stride_b, int32_t optimizer, float lr, float eps,
-                                   int32_t stochastic_rounding, uint64_t sr_seed, void *scratch,
-                                   int64_t scratch_bytes, void *stream) {
+                                   int32_t stochastic_rounding, uint64_t sr_seed,
+                                   int64_t max_table_rows, void *scratch, int64_t scratch_bytes,
+                                   int32_t plan_ready, void *stream) {
     if (!weights || !table_row_offsets || !offsets || !grad_out || (!indices && n_indices > 0))
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
@@ -696,10 +702,8 @@ extern "C" int pb200_tbe_bwd_fused(void *weights, int32_t weights_type, float *s
     op.stochastic = (weights_type == PB200_W_F16) && stochastic_rounding;
     op.sr_seed = sr_seed;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool i64 = idx_type == PB200_IDX_I64;
+    const bool ready = plan_ready != 0;
     if (weights_type == PB200_W_F32)
-        return i64 ? bwd_exact<long long, float>(p, op, scratch, scratch_bytes, st)
-                   : bwd_exact<int, float>(p, op, scratch, scratch_bytes, st);
-    return i64 ? bwd_exact<long long, __half>(p, op, scratch, scratch_bytes, st)
-               : bwd_exact<int, __half>(p, op, scratch, scratch_bytes, st);
+        return bwd_exact<float>(p, op, idx_type, max_table_rows, scratch, scratch_bytes, ready, st);
+    return bwd_exact<__half>(p, op, idx_type, max_table_rows, scratch, scratch_bytes, ready, st);
 }

@@ -16,6 +16,8 @@ struct pb200_host_ctx {
     float *d_out[2];
     cudaStream_t s_h2d, s_k, s_d2h;
     cudaEvent_t ev_h2d[2], ev_k[2], ev_d2h[2], ev_bwd[2];
+    void *bwd_scratch;          // sort plan + reducer scratch of the backward (grown on first use)
+    long long bwd_scratch_bytes;
 };
 
 using namespace pb200;
@@ -69,6 +71,7 @@ extern "C" int pb200_host_ctx_destroy(pb200_host_ctx *c) {
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    if (c->bwd_scratch) cudaFree(c->bwd_scratch);
     free(c);
     return PB200_OK;
 }
@@ -80,7 +83,6 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
                                    const int64_t *offsets_host, int64_t batch, int32_t pool_mode,
                                    float *out_host, int32_t out_layout, int32_t tables_per_group,
                                    int32_t do_bwd, float bwd_scale) {
-    (void)table_row_offsets_host;
     if (!c || !weights_dev || !table_row_offsets_dev || !indices_host || !offsets_host || !out_host)
         return PB200_EINVAL;
     if (num_tables < 1 || dim != c->dim || batch < 1 || tables_per_group < 1) return PB200_EINVAL;
@@ -88,6 +90,25 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
     if ((long long)tables_per_group * batch > c->max_bags) return PB200_EINVAL;
     // bulk staging wants absolute even index positions 16 B-aligned: keep batch even or fall back
     const int algo = PB200_FWD_AUTO;
+    if (do_bwd) {
+        // the backward is the same SORTED pipeline the device-resident path uses (sort plan + one
+        // segmented reduce); its scratch belongs to the context and is sized for the largest group
+        long long need = 0;
+        for (int t0 = 0; t0 < num_tables; t0 += tables_per_group) {
+            const int tg = (t0 + tables_per_group <= num_tables) ? tables_per_group : num_tables - t0;
+            const long long n = offsets_host[(long long)(t0 + tg) * batch] - offsets_host[(long long)t0 * batch];
+            const long long b = pb200_tbe_bwd_scratch_bytes(n, tg, batch, 0, PB200_BWD_SORTED);
+            if (b > need) need = b;
+        }
+        if (need > c->bwd_scratch_bytes) {
+            PB200_CUDA_TRY(cudaStreamSynchronize(c->s_k));
+            if (c->bwd_scratch) cudaFree(c->bwd_scratch);
+            c->bwd_scratch = nullptr;
+            c->bwd_scratch_bytes = 0;
+            PB200_CUDA_TRY(cudaMalloc(&c->bwd_scratch, (size_t)need));
+            c->bwd_scratch_bytes = need;
+        }
+    }
     int g = 0;
     for (int t0 = 0; t0 < num_tables; t0 += tables_per_group, ++g) {
         const int b = g & 1;
@@ -96,6 +117,12 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
         const long long i_lo = offsets_host[bag0], i_hi = offsets_host[bag0 + nb];
         const long long n = i_hi - i_lo;
         if (n < 0 || i_hi > n_indices || n > c->max_idx) return PB200_EINVAL;
+        long long max_rows = 0;   // bound of the group's largest table (0 = unknown: full 32-bit sort)
+        if (table_row_offsets_host)
+            for (int t = t0; t < t0 + tg; ++t) {
+                const long long r = table_row_offsets_host[t + 1] - table_row_offsets_host[t];
+                if (r > max_rows) max_rows = r;
+            }
         // staging buffer b must be free: its previous D2H (group g-2) finished
         if (g >= 2) {
             PB200_CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));
@@ -123,9 +150,11 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
             // training step: the pooled vectors double as the incoming gradient (in a real model
             // dOut is produced on the device by the layers above); scatter-add into the arena
             rc = pb200_tbe_bwd(weights_dev, table_row_offsets_dev + t0, tg, dim,
-                               c->d_idx[b] + pad - i_lo, i_hi, c->d_off[b], batch, PB200_IDX_I64,
+                               c->d_idx[b] + pad - i_lo, n, c->d_off[b], batch, PB200_IDX_I64,
                                nullptr, pool_mode, c->d_out[b], st_t, st_b, bwd_scale,
-                               PB200_BWD_ATOMIC, nullptr, 0, c->s_k);
+                               n > 0 ? PB200_BWD_SORTED : PB200_BWD_ATOMIC, max_rows,
+                               n > 0 ? c->bwd_scratch : nullptr, n > 0 ? c->bwd_scratch_bytes : 0, 0,
+                               c->s_k);
             if (rc != PB200_OK) return rc;
             PB200_CUDA_TRY(cudaEventRecord(c->ev_bwd[b], c->s_k));
         }

@@ -1,0 +1,479 @@
+// radix_sort.cu — builds the sort plan of the EmbeddingBag backward (sort_plan.cuh): a hand-written LSD
+// radix sort for sm_100a that sorts every table's lookups by row, fused with the construction of the
+// (row, gradient offset) pairs.  No library kernel, no host round trip.
+//
+// Replaces, on the backward the reference drives at train/comms/pt/pytorch_dist_backend.py:849-857 /
+// dlrm.py:1296 / split_table_batched_embeddings_ops.py:318-324, the cub::DeviceRadixSort::SortPairs call
+// (plus the separate pair-build kernel and the D2H of the table bounds) of the first version.
+//
+// What makes this sort different from a general one:
+//  * the table of a lookup is known from its POSITION (the request is table-major), so the sort is
+//    segmented per table and only the table-relative row is a key: 20 bits for a 1 M-row table — two
+//    passes of 10 bits instead of the three to four 8-bit passes a generic 32-bit sort needs for
+//    chunk-relative arena rows;
+//  * the first pass reads the int64/int32 indices directly and derives the value (the gradient row of the
+//    lookup's bag) from the offsets staged in shared memory: unsorted pairs are never written;
+//  * the last pass adds the table's first arena row and writes keys / values as two arrays, the form the
+//    segmented reducers read: the result is one globally sorted array over all tables, so the reducers
+//    run as ONE launch, with no chunk plan on the host.
+//
+// One pass = three kernels over tiles (a tile = the lookups of `tile_bags` consecutive bags of one table,
+// grid = tiles x tables, all sizes host-known):
+//   radix_hist_kernel     digit histogram of the tile -> hist[table][tile][bin]
+//   radix_scan_kernel     per (table, bin): exclusive prefix over the tiles, bin totals
+//   radix_scatter_kernel  re-reads the tile in sub-tiles of 4096 lookups; per-warp ranking with
+//                         match.any (a warp's lanes with equal digits elect a leader that bumps the warp's
+//                         private counter: no atomics, deterministic), cross-warp and cross-bin scans in
+//                         shared memory, the sub-tile is permuted into digit order in shared memory and
+//                         written out as runs of consecutive addresses per bin.
+// The sort is stable, so the order of equal rows — hence the summation order of the reducers — is fixed:
+// lookups of a row are summed in request order (bag-major), run to run identical.
+//
+// Traffic per lookup for a 2-pass plan with int64 indices: 8 (hist 1: index) + 8 + 8 (scatter 1: index in,
+// pair out) + 8 (hist 2: pair) + 8 + 8 (scatter 2) = 48 B, against the 1057.6 B per lookup of the
+// backward's algorithmic figure.
+#include "sort_plan.cuh"
+
+namespace pb200 {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 16;                                  // lookups per thread per sub-tile
+constexpr int kSortSub = kSortThreads * kSortItems;             // 4096 lookups per sub-tile
+
+struct SortArgs {
+    const void *indices;
+    const void *offsets;
+    const long long *table_row_offsets;
+    const float *psw;
+    long long batch;
+    long long go_stride_t, go_stride_b;
+    int mean;
+    int t_base;              // first table of this launch (blockIdx.y is relative to it)
+    int tile_bags, tiles_per_table;
+    int shift, bits;
+    const uint2 *src;        // pairs of the previous pass (nullptr: first pass, read the request)
+    uint2 *dst_pairs;        // pairs for the next pass (nullptr: last pass)
+    unsigned *dst_keys;      // last pass: arena rows, sorted
+    unsigned *dst_vals;
+    unsigned *goff_of;       // weighted / mean: per-position side arrays, written by the first pass
+    float *w_of;
+    unsigned *hist;          // [T][tiles_per_table][1 << bits]
+    unsigned *bin_total;     // [T][1 << bits]
+    long long *count;        // out: offsets[T * B] - offsets[0]
+    int num_tables;
+};
+
+// Positions p0, p1 are absolute (they address `indices` / `psw`, which the caller may have shifted so that
+// offsets need not start at 0); the plan's arrays are addressed relative to origin = offsets[0].
+template <typename index_t>
+__device__ __forceinline__ void tile_range(const SortArgs &a, int t, int tile, long long &bag0,
+                                           int &nb, long long &p0, long long &p1, long long &origin) {
+    const index_t *off = (const index_t *)a.offsets;
+    origin = (long long)off[0];
+    const long long tb0 = (long long)t * a.batch;
+    const long long b0 = (long long)tile * a.tile_bags;
+    long long b1 = b0 + a.tile_bags;
+    if (b1 > a.batch) b1 = a.batch;
+    bag0 = tb0 + b0;
+    nb = (int)(b1 - b0);
+    p0 = (long long)off[tb0 + b0];
+    p1 = (long long)off[tb0 + b1];
+}
+
+// ---- K1: digit histogram of one tile ---------------------------------------------------------------
+template <typename index_t, bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const SortArgs a) {
+    extern __shared__ unsigned s_hist[];
+    const int bins = 1 << a.bits;
+    const unsigned mask = (unsigned)bins - 1u;
+    const int t = a.t_base + blockIdx.y;
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    long long bag0, p0, p1, origin;
+    int nb;
+    tile_range<index_t>(a, t, tile, bag0, nb, p0, p1, origin);
+    for (int b = threadIdx.x; b < bins; b += kSortThreads) s_hist[b] = 0;
+    if (FIRST && t == 0 && tile == 0 && threadIdx.x == 0) {
+        const index_t *off = (const index_t *)a.offsets;
+        *a.count = (long long)off[(long long)a.num_tables * a.batch] - origin;
+    }
+    __syncthreads();
+    const index_t *idx = (const index_t *)a.indices;
+    constexpr int U = 4;
+    for (long long base = p0; base < p1; base += (long long)kSortThreads * U) {   // CTA-uniform trip count
+        unsigned d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pos = base + (long long)u * kSortThreads + threadIdx.x;
+            d[u] = 0xffffffffu;
+            if (pos < p1) {
+                const unsigned key = FIRST ? (unsigned)ld_index<index_t>(idx + pos) : a.src[pos - origin].x;
+                d[u] = (key >> a.shift) & mask;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned peers = __match_any_sync(0xffffffffu, d[u]);
+            if (d[u] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d[u]], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * bins;
+    for (int b = threadIdx.x; b < bins; b += kSortThreads) h[b] = s_hist[b];
+}
+
+// ---- K2: per (table, bin) exclusive prefix over the tiles --------------------------------------------
+// grid (ceil(bins / 32), tables); a warp = one slice of the tiles, a lane = one bin
+__global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(const SortArgs a) {
+    __shared__ unsigned s_sum[kSortWarps][32];
+    const int bins = 1 << a.bits;
+    const int t = a.t_base + blockIdx.y;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const int nt = a.tiles_per_table;
+    const int per = (nt + kSortWarps - 1) / kSortWarps;
+    const int lo = slice * per;
+    const int hi = min(nt, lo + per);
+    unsigned *h = a.hist + (size_t)t * nt * bins + b;
+    unsigned sum = 0;
+    if (b < bins)
+        for (int i = lo; i < hi; ++i) sum += h[(size_t)i * bins];
+    s_sum[slice][lane] = sum;
+    __syncthreads();
+    unsigned run = 0, total = 0;
+#pragma unroll
+    for (int s = 0; s < kSortWarps; ++s) {
+        const unsigned v = s_sum[s][lane];
+        if (s < slice) run += v;
+        total += v;
+    }
+    if (b < bins) {
+        for (int i = lo; i < hi; ++i) {
+            const unsigned v = h[(size_t)i * bins];
+            h[(size_t)i * bins] = run;
+            run += v;
+        }
+        if (slice == 0) a.bin_total[(size_t)t * bins + b] = total;
+    }
+}
+
+// exclusive scan of n <= 256 * per values in shared memory, in place; all threads of the CTA call it
+__device__ __forceinline__ void block_excl_scan(unsigned *v, int n, unsigned *s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + kSortThreads - 1) / kSortThreads;
+    const int lo = min(n, (int)threadIdx.x * per);
+    const int hi = min(n, lo + per);
+    unsigned sum = 0;
+    for (int i = lo; i < hi; ++i) sum += v[i];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned w = lane < kSortWarps ? s_warp[lane] : 0u;
+        unsigned wi = w;
+#pragma unroll
+        for (int o = 1; o < kSortWarps; o <<= 1) {
+            const unsigned x = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += x;
+        }
+        if (lane < kSortWarps) s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned run = s_warp[warp] + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned x = v[i];
+        v[i] = run;
+        run += x;
+    }
+    __syncthreads();
+}
+
+__host__ __device__ __forceinline__ size_t union_bytes(int bins) {
+    const size_t a = (size_t)kSortWarps * bins * 4, b = (size_t)kSortSub * 8;
+    return a > b ? a : b;
+}
+
+// ---- K3: rank and scatter one tile -------------------------------------------------------------------
+// dynamic shared memory: { wh[kSortWarps][bins] (ranking)  UNION  stage[kSortSub] uint2 (permute) }
+//                        | bin_base[bins] | sub_start[bins + 1] | offs[tile_bags + 1] (FIRST)
+template <typename index_t, bool FIRST, bool LAST, bool SIDE>
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ unsigned s_warp[kSortWarps];
+    const int bins = 1 << a.bits;
+    const unsigned mask = (unsigned)bins - 1u;
+    unsigned *wh = (unsigned *)s_raw;
+    uint2 *stage = (uint2 *)s_raw;               // the counters are dead once the staging positions are known
+    unsigned *bin_base = (unsigned *)(s_raw + union_bytes(bins));
+    unsigned *sub_start = bin_base + bins;
+    unsigned *offs = sub_start + bins + 1;
+
+    const int t = a.t_base + blockIdx.y;
+    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    long long bag0, p0, p1, origin;
+    int nb;
+    tile_range<index_t>(a, t, tile, bag0, nb, p0, p1, origin);
+    if (p1 <= p0) return;                                           // CTA-uniform
+    const index_t *off = (const index_t *)a.offsets;
+    const index_t *idx = (const index_t *)a.indices;
+    const long long table_p0 = (long long)off[(long long)t * a.batch] - origin;
+    const unsigned row_base = LAST ? (unsigned)a.table_row_offsets[t] : 0u;
+
+    // where this tile's lookups of every bin go: table start + bins before + same bin in earlier tiles
+    {
+        const unsigned *bt = a.bin_total + (size_t)t * bins;
+        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] = bt[b];
+        __syncthreads();
+        block_excl_scan(bin_base, bins, s_warp);
+        const unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * bins;
+        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] += (unsigned)table_p0 + h[b];
+    }
+    if (FIRST) {
+        // bag boundaries of the tile relative to p0; bag j of the tile covers [offs[j], offs[j + 1])
+        for (int j = threadIdx.x; j <= nb; j += kSortThreads) offs[j] = (unsigned)((long long)off[bag0 + j] - p0);
+    }
+    __syncthreads();
+
+    for (long long sub = p0; sub < p1; sub += kSortSub) {
+        const int n_sub = (int)min((long long)kSortSub, p1 - sub);
+        for (int i = threadIdx.x; i < kSortWarps * bins; i += kSortThreads) wh[i] = 0;
+        __syncthreads();
+
+        // ---- load + per-warp ranking: warp w owns lookups [w * 32 * ITEMS, +32 * ITEMS) of the sub-tile
+        unsigned key[kSortItems], val[kSortItems], rank[kSortItems];
+        unsigned *my_wh = wh + warp * bins;
+        const long long wbase = sub + (long long)warp * 32 * kSortItems + lane;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const long long pos = wbase + k * 32;
+            key[k] = 0xffffffffu;
+            val[k] = 0;
+            if (pos < p1) {
+                if (FIRST) {
+                    key[k] = (unsigned)ld_index<index_t>(idx + pos);
+                } else {
+                    const uint2 pr = a.src[pos - origin];
+                    key[k] = pr.x;
+                    val[k] = pr.y;
+                }
+            }
+        }
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < kSortItems; ++k) {
+                const long long pos = wbase + k * 32;
+                if (pos < p1) {
+                    // last bag boundary <= pos (empty bags repeat a boundary: the last one is the bag)
+                    const unsigned rel = (unsigned)(pos - p0);
+                    int j = 0;
+                    for (int step = a.tile_bags >> 1; step >= 1; step >>= 1) {
+                        const int c = j + step;
+                        if (c <= nb && offs[c] <= rel) j = c;
+                    }
+                    // c <= nb admits offs[nb] == n_tile > rel only when false, so j < nb here
+                    const long long gb = bag0 + j;
+                    const long long tt = t;
+                    const long long bb = gb - tt * a.batch;
+                    const unsigned goff4 = (unsigned)((tt * a.go_stride_t + bb * a.go_stride_b) >> 2);
+                    if (SIDE) {
+                        val[k] = (unsigned)(pos - origin);
+                        const float inv = a.mean ? 1.f / (float)(offs[j + 1] - offs[j]) : 1.f;
+                        a.goff_of[pos - origin] = goff4;
+                        a.w_of[pos - origin] = (a.psw ? a.psw[pos] : 1.f) * inv;
+                    } else {
+                        val[k] = goff4;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const bool valid = (wbase + k * 32) < p1;
+            const unsigned d = valid ? ((key[k] >> a.shift) & mask) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned prev = 0;
+            if (valid && lane == leader) {
+                prev = my_wh[d];
+                my_wh[d] = prev + (unsigned)__popc(peers);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            rank[k] = prev + (unsigned)__popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per bin: exclusive prefix over the warps (in place), count of the CTA -> sub_start
+        for (int b = threadIdx.x; b < bins; b += kSortThreads) {
+            unsigned run = 0;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const unsigned v = wh[w * bins + b];
+                wh[w * bins + b] = run;
+                run += v;
+            }
+            sub_start[b] = run;
+        }
+        if (threadIdx.x == 0) sub_start[bins] = (unsigned)n_sub;
+        __syncthreads();
+        block_excl_scan(sub_start, bins, s_warp);
+
+        // ---- permute the sub-tile into digit order in shared memory (over the counters: positions first)
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            if ((wbase + k * 32) < p1) {
+                const unsigned d = (key[k] >> a.shift) & mask;
+                rank[k] += sub_start[d] + my_wh[d];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k)
+            if ((wbase + k * 32) < p1) stage[rank[k]] = make_uint2(key[k], val[k]);
+        __syncthreads();
+
+        // ---- write out: consecutive threads -> consecutive addresses inside a bin's run
+        for (int i = threadIdx.x; i < n_sub; i += kSortThreads) {
+            const uint2 pr = stage[i];
+            const unsigned d = (pr.x >> a.shift) & mask;
+            const unsigned o = bin_base[d] + ((unsigned)i - sub_start[d]);
+            if (LAST) {
+                a.dst_keys[o] = pr.x + row_base;
+                a.dst_vals[o] = pr.y;
+            } else {
+                a.dst_pairs[o] = pr;
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] += sub_start[b + 1] - sub_start[b];
+        // the barrier after the next sub-tile's counter reset orders this update before its readers
+    }
+}
+
+static size_t scatter_smem_bytes(int bits, int tile_bags, bool first) {
+    const size_t bins = (size_t)1 << bits;
+    size_t bytes = union_bytes((int)bins) + (2 * bins + 1) * 4;
+    if (first) bytes += ((size_t)tile_bags + 1) * 4;
+    return bytes;
+}
+
+template <typename Kern>
+static int set_smem(Kern k, size_t bytes) {
+    if (bytes > 48 * 1024)
+        PB200_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PB200_OK;
+}
+
+template <typename index_t, bool FIRST, bool LAST>
+static int launch_pass(const SortArgs &a, bool side, dim3 grid, cudaStream_t st) {
+    const size_t hist_smem = ((size_t)1 << a.bits) * 4;
+    radix_hist_kernel<index_t, FIRST><<<grid, kSortThreads, hist_smem, st>>>(a);
+    PB200_LAUNCH_CHECK();
+    dim3 sgrid((unsigned)(((1u << a.bits) + 31) / 32), grid.y);
+    radix_scan_kernel<<<sgrid, kSortThreads, 0, st>>>(a);
+    PB200_LAUNCH_CHECK();
+    const size_t smem = scatter_smem_bytes(a.bits, a.tile_bags, FIRST);
+    int rc;
+    if (FIRST && side) {
+        auto k = radix_scatter_kernel<index_t, FIRST, LAST, true>;
+        if ((rc = set_smem(k, smem)) != PB200_OK) return rc;
+        k<<<grid, kSortThreads, smem, st>>>(a);
+    } else {
+        auto k = radix_scatter_kernel<index_t, FIRST, LAST, false>;
+        if ((rc = set_smem(k, smem)) != PB200_OK) return rc;
+        k<<<grid, kSortThreads, smem, st>>>(a);
+    }
+    PB200_LAUNCH_CHECK();
+    count_launch(3);
+    return PB200_OK;
+}
+
+template <typename index_t>
+static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void *plan,
+                             const PlanLayout &L, cudaStream_t st) {
+    const bool side = (p.psw != nullptr) || p.mean;
+    const SortGeom g = sort_geometry(p.n_indices, p.num_tables, p.batch, max_table_rows);
+    unsigned char *base = (unsigned char *)plan;
+    // tables per launch: all of them by default; PB200_SORT_GROUP = g runs the passes group by group
+    // (the group's pairs then stay closer to L2 between the kernels of a pass)
+    static const int group_env = [] {
+        const char *e = getenv("PB200_SORT_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    int group = group_env > 0 ? group_env : p.num_tables;
+    if (group > 65535) group = 65535;
+
+    SortArgs a{};
+    a.indices = p.indices;
+    a.offsets = p.offsets;
+    a.table_row_offsets = p.table_row_offsets;
+    a.psw = p.psw;
+    a.batch = p.batch;
+    a.go_stride_t = p.go_stride_t;
+    a.go_stride_b = p.go_stride_b;
+    a.mean = p.mean;
+    a.tile_bags = g.tile_bags;
+    a.tiles_per_table = g.tiles_per_table;
+    a.goff_of = (unsigned *)(base + L.goff_of);
+    a.w_of = (float *)(base + L.w_of);
+    a.hist = (unsigned *)(base + L.hist);
+    a.bin_total = (unsigned *)(base + L.bin_total);
+    a.count = (long long *)(base + L.count);
+    a.num_tables = p.num_tables;
+    unsigned *keys = (unsigned *)(base + L.keys);
+    unsigned *vals = (unsigned *)(base + L.vals);
+    // ping-pong between the pair buffer and (as 8 B pairs) the final key/value area, arranged so that the
+    // last pass reads the pair buffer and writes keys / vals:  P = 1: request -> out;  P = 2: request ->
+    // tmp -> out;  P = 3: request -> out-as-pairs -> tmp -> out; ...
+    uint2 *tmp = (uint2 *)(base + L.tmp);
+    uint2 *out_as_pairs = (uint2 *)(base + L.keys);   // keys | vals are adjacent: n * 8 bytes
+
+    for (int t0 = 0; t0 < p.num_tables; t0 += group) {
+        const int tg = (t0 + group <= p.num_tables) ? group : p.num_tables - t0;
+        dim3 grid((unsigned)g.tiles_per_table, (unsigned)tg);
+        a.t_base = t0;
+        for (int ps = 0; ps < g.passes; ++ps) {
+            const bool first = ps == 0, last = ps == g.passes - 1;
+            a.shift = g.shift[ps];
+            a.bits = g.bits[ps];
+            // pass ps writes buffer (passes - 1 - ps) & 1: 0 = out area, 1 = tmp
+            uint2 *wr = ((g.passes - 1 - ps) & 1) ? tmp : out_as_pairs;
+            const uint2 *rd = ((g.passes - ps) & 1) ? tmp : out_as_pairs;
+            a.src = first ? nullptr : rd;
+            a.dst_pairs = last ? nullptr : wr;
+            a.dst_keys = last ? keys : nullptr;
+            a.dst_vals = last ? vals : nullptr;
+            int rc;
+            if (first && last) rc = launch_pass<index_t, true, true>(a, side, grid, st);
+            else if (first) rc = launch_pass<index_t, true, false>(a, side, grid, st);
+            else if (last) rc = launch_pass<index_t, false, true>(a, side, grid, st);
+            else rc = launch_pass<index_t, false, false>(a, side, grid, st);
+            if (rc != PB200_OK) return rc;
+        }
+    }
+    return PB200_OK;
+}
+
+int build_sort_plan(const BwdParams &p, int idx_type, long long max_table_rows, void *plan,
+                    const PlanLayout &L, cudaStream_t st) {
+    if (p.n_indices <= 0 || p.n_bags <= 0) return PB200_OK;
+    // positions, gradient-row offsets (float4 units) and arena rows travel as 32-bit values
+    if (p.n_indices >= 0xffffffffll) return PB200_EUNSUPPORTED;
+    {
+        const long long last = (long long)(p.num_tables - 1) * p.go_stride_t + (p.batch - 1) * p.go_stride_b + p.dim;
+        if ((last >> 2) >= 0xffffffffll) return PB200_EUNSUPPORTED;
+    }
+    if (idx_type == PB200_IDX_I64) return build_sort_plan_t<long long>(p, max_table_rows, plan, L, st);
+    if (idx_type == PB200_IDX_I32) return build_sort_plan_t<int>(p, max_table_rows, plan, L, st);
+    return PB200_EINVAL;
+}
+
+}  // namespace pb200

@@ -159,6 +159,8 @@ def tbe_forward(arena: TableArena, indices: torch.Tensor, offsets: torch.Tensor,
     psw = None
     if per_sample_weights is not None:
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+        if psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must match indices")
     if batch == 0:
         return out
     if arena.weights.dtype == torch.float16:
@@ -195,14 +197,102 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+def _layout_strides(layout: str, T: int, D: int, batch: int):
+    if layout == "BTD":
+        return D, T * D
+    if layout == "TBD":
+        return batch * D, D
+    raise PB200Error("layout must be 'BTD' or 'TBD'")
+
+
+@dataclass
+class SortPlan:
+    """The index-only half of the sort-based backward (C ABI section 3c), built ahead of the gradient —
+    typically on a side stream while the forward lookup of the same request runs.  `buf` is the scratch
+    buffer the backward call consumes with plan_ready = 1; `ready` is recorded on the building stream."""
+    buf: torch.Tensor
+    signature: tuple
+    ready: Optional[torch.cuda.Event]
+    exact: bool
+
+
+def _plan_signature(indices, offsets, T, D, batch, layout, mode, psw):
+    return (indices.data_ptr(), indices.numel(), offsets.data_ptr(), T, D, batch, layout, mode,
+            None if psw is None else psw.data_ptr())
+
+
+def tbe_plan(row_offsets: torch.Tensor, num_tables: int, dim: int, indices: torch.Tensor,
+             offsets: torch.Tensor, batch: int, max_table_rows: int, layout: str = "BTD",
+             mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None,
+             exact: bool = False, stream: Optional[torch.cuda.Stream] = None,
+             buf: Optional[torch.Tensor] = None) -> SortPlan:
+    """Sort the lookups of a TBE request by row (pb200_tbe_plan_build).  With `stream` the sort is
+    queued on that stream after everything already queued on the current one (inputs are ready
+    there), so it overlaps the forward lookup; tbe_backward(..., plan=) then waits for it.
+    `exact` sizes the buffer for tbe_backward_fused / algo="exact".  `buf`: reuse a buffer of a
+    previous plan of the same shape (steady-state training loops)."""
+    _need_cuda(row_offsets, indices, offsets, per_sample_weights)
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    T, D = num_tables, dim
+    if offsets.numel() != T * batch + 1:
+        raise PB200Error("offsets must have T*batch+1 entries")
+    st_t, st_b = _layout_strides(layout, T, D, batch)
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1)
+        if psw.dtype != torch.float32 or psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must be fp32 and match indices")
+    lib = _cabi.load()
+    if exact:
+        nbytes = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, batch, D))
+    else:
+        nbytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, 0, BWD_SORTED))
+    dev = indices.device
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    run_on = stream if stream is not None else cur
+    if stream is not None:
+        stream.wait_stream(cur)
+        for t in (buf, indices, offsets, row_offsets, psw):
+            if t is not None:
+                t.record_stream(stream)
+    rc = lib.pb200_tbe_plan_build(buf.data_ptr(), nbytes, row_offsets.data_ptr(), int(max_table_rows), T, D,
+                                  _ptr(indices), indices.numel(), _ptr(offsets), batch, it, _ptr(psw),
+                                  _MODE[mode], st_t, st_b, run_on.cuda_stream)
+    _cabi.check(rc, "pb200_tbe_plan_build")
+    ready = None
+    if stream is not None:
+        ready = torch.cuda.Event()
+        ready.record(stream)
+    return SortPlan(buf, _plan_signature(indices, offsets, T, D, batch, layout, mode, psw), ready, exact)
+
+
+def _use_plan(plan: SortPlan, sig: tuple, need_bytes: int, dev) -> int:
+    if plan.signature != sig:
+        raise PB200Error("the sort plan was built for another request (indices / offsets / layout / mode / "
+                         "per_sample_weights differ)")
+    if plan.buf.numel() < need_bytes:
+        raise PB200Error("the sort plan buffer is too small for this backward variant (build it with exact=True)")
+    if plan.ready is not None:
+        torch.cuda.current_stream(dev).wait_event(plan.ready)
+    return plan.buf.data_ptr()
+
+
 def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, dim: int,
                  indices: torch.Tensor, offsets: torch.Tensor, batch: int,
                  grad_out: torch.Tensor, layout: str = "BTD", scale: float = 1.0,
                  mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None,
-                 algo: str = "auto") -> None:
+                 algo: str = "auto", max_table_rows: int = 0,
+                 plan: Optional[SortPlan] = None) -> None:
     """dst[row(t, idx[i])] += scale * w_i * grad_out[(t, bag(i))].  dst is either a dense grad
     buffer shaped like the arena (scale=1) or the arena itself (scale=-lr, fused SGD).
-    Reference: autograd backward driven at pytorch_dist_backend.py:849-857 / dlrm.py:1296."""
+    Reference: autograd backward driven at pytorch_dist_backend.py:849-857 / dlrm.py:1296.
+    max_table_rows: rows of the largest table (fixes the radix passes of the sort; 0 = the arena's
+    row count, always a valid bound).  plan: a SortPlan built by tbe_plan for this request — the call
+    is then the segmented reduce alone."""
     _need_cuda(dst, row_offsets, indices, offsets, grad_out, per_sample_weights)
     indices = indices.contiguous().view(-1)
     offsets = offsets.contiguous().view(-1)
@@ -213,30 +303,42 @@ def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, 
     grad_out = grad_out.contiguous()
     if grad_out.dtype != torch.float32 or grad_out.numel() != T * batch * D:
         raise PB200Error("grad_out must be fp32 with T*batch*dim elements")
-    if layout == "BTD":
-        st_t, st_b = D, T * D
-    elif layout == "TBD":
-        st_t, st_b = batch * D, D
-    else:
-        raise PB200Error("layout must be 'BTD' or 'TBD'")
+    st_t, st_b = _layout_strides(layout, T, D, batch)
     if dst.dtype != torch.float32:
         raise PB200Error("tbe_backward scatters into fp32 rows; fp16 tables use tbe_backward_fused")
-    lib = _cabi.load()
-    a = _BWD_ALGO[algo]
-    scratch_ptr, scratch_bytes = None, 0
-    if a in (BWD_SORTED, BWD_AUTO):
-        scratch_bytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, dst.shape[0], BWD_SORTED))
-        scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
-    elif a == BWD_EXACT:
-        scratch_bytes = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, D))
-        scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
+    if dst.dim() != 2 or dst.shape[1] != D or not dst.is_contiguous():
+        raise PB200Error("dst must be a contiguous fp32 [rows, dim] tensor")
     psw = None
     if per_sample_weights is not None:
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+        if psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must match indices")
+    lib = _cabi.load()
+    a = _BWD_ALGO[algo]
+    if a == BWD_AUTO:
+        # a plan says which reducer it was sized for; otherwise the sort pays from ~64 k lookups on
+        # (below that the launch latency of the sort passes exceeds what the atomics cost)
+        if plan is not None:
+            a = BWD_EXACT if plan.exact else BWD_SORTED
+        else:
+            a = BWD_SORTED if indices.numel() >= 65536 else BWD_ATOMIC
+    scratch_ptr, scratch_bytes = None, 0
+    if a in (BWD_SORTED, BWD_AUTO):
+        scratch_bytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, dst.shape[0], BWD_SORTED))
+    elif a == BWD_EXACT:
+        scratch_bytes = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, batch, D))
+    if plan is not None:
+        if a == BWD_ATOMIC:
+            raise PB200Error("the atomic backward takes no sort plan")
+        scratch_ptr = _use_plan(plan, _plan_signature(indices, offsets, T, D, batch, layout, mode, psw),
+                                scratch_bytes, dst.device)
+    elif scratch_bytes:
+        scratch_ptr = _scratch(dst.device, scratch_bytes).data_ptr()
+    mtr = int(max_table_rows) if max_table_rows and max_table_rows > 0 else int(dst.shape[0])
     rc = lib.pb200_tbe_bwd(dst.data_ptr(), row_offsets.data_ptr(), T, D, _ptr(indices),
                            indices.numel(), _ptr(offsets), batch, it, _ptr(psw), _MODE[mode],
-                           grad_out.data_ptr(), st_t, st_b, float(scale), a, scratch_ptr,
-                           scratch_bytes, _stream_ptr(dst))
+                           grad_out.data_ptr(), st_t, st_b, float(scale), a, mtr, scratch_ptr,
+                           scratch_bytes, 1 if plan is not None else 0, _stream_ptr(dst))
     _cabi.check(rc, "pb200_tbe_bwd")
 
 
@@ -246,11 +348,13 @@ def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tab
                        eps: float = 1.0e-8, state: Optional[torch.Tensor] = None,
                        layout: str = "BTD", mode: str = "sum",
                        per_sample_weights: Optional[torch.Tensor] = None,
-                       stochastic_rounding: bool = False, sr_seed: int = 0) -> None:
+                       stochastic_rounding: bool = False, sr_seed: int = 0,
+                       max_table_rows: int = 0, plan: Optional[SortPlan] = None) -> None:
     """Backward with the optimizer fused in, one deterministic update per touched row (C ABI §3b):
     exact_sgd `w -= lr*g` or exact_row_wise_adagrad `m += mean(g^2); w -= lr/(sqrt(m)+eps)*g`,
     fp32 or fp16 tables.  Stands in for the fused backward of fbgemm's TBE op that the reference
-    builds at comms_utils.py:1995-2017 / split_table_batched_embeddings_ops.py:279-301."""
+    builds at comms_utils.py:1995-2017 / split_table_batched_embeddings_ops.py:279-301.
+    max_table_rows / plan: as for tbe_backward (the plan must have been built with exact=True)."""
     _need_cuda(weights, row_offsets, indices, offsets, grad_out, per_sample_weights, state)
     if weights.dtype not in _W_TYPE or weights.dim() != 2 or not weights.is_contiguous():
         raise PB200Error("weights must be a contiguous fp32 or fp16 [rows, dim] tensor")
@@ -265,30 +369,34 @@ def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tab
     offsets = offsets.contiguous().view(-1)
     it = _idx_type(indices, offsets)
     T, D = num_tables, dim
+    if weights.shape[1] != D:
+        raise PB200Error("weights must be [rows, dim]")
     if offsets.numel() != T * batch + 1:
         raise PB200Error("offsets must have T*batch+1 entries")
     grad_out = grad_out.contiguous()
     if grad_out.dtype != torch.float32 or grad_out.numel() != T * batch * D:
         raise PB200Error("grad_out must be fp32 with T*batch*dim elements")
-    if layout == "BTD":
-        st_t, st_b = D, T * D
-    elif layout == "TBD":
-        st_t, st_b = batch * D, D
-    else:
-        raise PB200Error("layout must be 'BTD' or 'TBD'")
+    st_t, st_b = _layout_strides(layout, T, D, batch)
     psw = None
     if per_sample_weights is not None:
         psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+        if psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must match indices")
     lib = _cabi.load()
-    sb = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, D))
-    scratch = _scratch(weights.device, sb)
+    sb = int(lib.pb200_tbe_bwd_fused_scratch_bytes(indices.numel(), T, batch, D))
+    if plan is not None:
+        scratch_ptr = _use_plan(plan, _plan_signature(indices, offsets, T, D, batch, layout, mode, psw), sb,
+                                weights.device)
+    else:
+        scratch_ptr = _scratch(weights.device, sb).data_ptr()
+    mtr = int(max_table_rows) if max_table_rows and max_table_rows > 0 else int(weights.shape[0])
     rc = lib.pb200_tbe_bwd_fused(weights.data_ptr(), _W_TYPE[weights.dtype], _ptr(state),
                                  row_offsets.data_ptr(), T, D, _ptr(indices), indices.numel(),
                                  _ptr(offsets), batch, it, _ptr(psw), _MODE[mode],
                                  grad_out.data_ptr(), st_t, st_b, opt, float(lr), float(eps),
                                  1 if stochastic_rounding else 0,
-                                 C.c_uint64(int(sr_seed) & (2 ** 64 - 1)), scratch.data_ptr(), sb,
-                                 _stream_ptr(weights))
+                                 C.c_uint64(int(sr_seed) & (2 ** 64 - 1)), mtr, scratch_ptr, sb,
+                                 1 if plan is not None else 0, _stream_ptr(weights))
     _cabi.check(rc, "pb200_tbe_bwd_fused")
 
 

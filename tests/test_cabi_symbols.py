@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_abi_loads_and_reports_errors_without_gpu():
     from param_b200 import _cabi
     lib = _cabi.load()
-    assert lib.pb200_abi_version() == 1
+    assert lib.pb200_abi_version() == 2
     assert b"invalid" in lib.pb200_error_string(-1)
     assert lib.pb200_launch_count() >= 0
     # argument validation happens before any CUDA call
@@ -53,3 +53,16 @@ def test_kernels_refuse_cpu_tensors():
     with pytest.raises(PB200Error):
         ops.embedding_bag_forward(torch.randn(4, 4), torch.zeros(2, dtype=torch.int64),
                                   torch.zeros(2, dtype=torch.int64))
+
+
+def test_no_library_sort_left():
+    """the backward's sort is hand-written (csrc/radix_sort.cu): no cub radix-sort kernel in the library"""
+    import shutil
+    import subprocess
+    import pytest
+    from param_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-sass", str(build.build_cuda())], capture_output=True, text=True).stdout
+    assert "DeviceRadixSort" not in out
+    assert "radix_scatter_kernel" in out
