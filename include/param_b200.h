@@ -294,6 +294,17 @@ int pb200_a2a_single(pb200_a2a_comm *comm, const void *in, int64_t total_in_byte
                      const int64_t *in_split_bytes, const int64_t *out_split_bytes,
                      int64_t out_window_off, void *out, void *stream);
 
+/* List form — dist.all_to_all(output_tensor_list, input_tensor_list).
+ * Replaces: backendFunctions.all_to_all   train/comms/pt/pytorch_dist_backend.py:207-260.
+ * in_ptrs[w] / in_bytes[w]: host arrays, the device block sent to rank w.  The block received from
+ * source r lands at byte offset out_window_offs[r] of THIS rank's window (out_bytes[r] bytes; an
+ * output tensor that lives in the window is written in place by the peer).  out_copy: NULL, or a
+ * host array of W device pointers — block r is then copied from the window to out_copy[r] on the
+ * stream (entries may be NULL).  No packing pass before, no unpacking pass after. */
+int pb200_a2a_list(pb200_a2a_comm *comm, const void *const *in_ptrs, const int64_t *in_bytes,
+                   const int64_t *out_window_offs, const int64_t *out_bytes,
+                   void *const *out_copy, void *stream);
+
 /* =========================================================================
  * 5. DLRM pooled-embedding exchange fused with the output permute
  * =========================================================================

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd",
     "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused", "pb200_tbe_plan_build",
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
-    "pb200_a2a_comm_error", "pb200_a2a_single",
+    "pb200_a2a_comm_error", "pb200_a2a_single", "pb200_a2a_list",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_tbe_fwd_a2a",
     "pb200_regroup_scratch_bytes", "pb200_regroup_sparse", "pb200_sparse_data_dist",
     "pb200_host_ctx_create", "pb200_host_ctx_destroy", "pb200_tbe_fwd_host", "pb200_tbe_step_host",
@@ -104,6 +104,7 @@ def load():
     sig("pb200_a2a_comm_config", C.c_int, vp, i32, C.c_double)
     sig("pb200_a2a_comm_error", C.c_int, vp, C.POINTER(i32))
     sig("pb200_a2a_single", C.c_int, vp, vp, i64, p_i64, p_i64, i64, vp, vp)
+    sig("pb200_a2a_list", C.c_int, vp, C.POINTER(vp), p_i64, p_i64, p_i64, C.POINTER(vp), vp)
     sig("pb200_a2a_pooled_fwd", C.c_int, vp, vp, i64, i64, i32, p_i64, p_i64, i64, vp)
     sig("pb200_a2a_pooled_bwd", C.c_int, vp, vp, i32, p_i64, p_i64, i64, vp)
     sig("pb200_tbe_fwd_a2a", C.c_int, vp, vp, vp, i32, i32, vp, i64, vp, i32, i32, p_i64, p_i64, i64, vp)

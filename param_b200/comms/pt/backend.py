@@ -67,13 +67,19 @@ class B200CommsMixin:
     _window_group = None
 
     # ---- window management -------------------------------------------------------------------
-    def _ensure_window(self, group=None, min_bytes: int = 0) -> PeerWindow:
+    def _ensure_window(self, group=None) -> PeerWindow:
+        """The peer window of `group`, mapped ONCE with PB200_WINDOW_BYTES (default 5 GB).  Mapping is a
+        collective (rendezvous + barrier), so it is never triggered from a rank-local size: a request
+        that does not fit raises on the rank that sees it (PeerWindow._staging_offset) with the knob to
+        turn, instead of re-mapping under the feet of the peers."""
         group = group if group is not None else dist.group.WORLD
-        if self._window is None or self._window_group is not group or self._window.window_bytes < min_bytes:
-            size = max(DEFAULT_WINDOW_BYTES, int(min_bytes))
-            self._window = PeerWindow.create(group, size, self.get_device())
+        if self._window is None or self._window_group is not group:
+            if self._window is not None:
+                self._window.close()
+            self._window = PeerWindow.create(group, DEFAULT_WINDOW_BYTES, self.get_device())
             self._window_group = group
-            logger.info("b200: mapped %d B peer window via %s", size, getattr(self._window, "mapping", "?"))
+            logger.info("b200: mapped %d B peer window via %s", DEFAULT_WINDOW_BYTES,
+                        getattr(self._window, "mapping", "?"))
         return self._window
 
     def _window_alloc(self, numel: int, dtype: torch.dtype) -> Optional[torch.Tensor]:
@@ -143,12 +149,11 @@ class B200CommsMixin:
         if not inp.is_cuda:
             raise PB200Error("the b200 backend moves CUDA tensors only (no CPU/gloo fallback)")
         win = self._ensure_window(group)
-        need = out.numel() * out.element_size()
-        if win.offset_of(out) is None and need > win.window_bytes:
-            win = self._ensure_window(group, need)
         if out.dtype != inp.dtype:
             raise PB200Error("all_to_all needs input and output of one dtype")
-        win.all_to_all_single(out, inp.contiguous().view(-1),
+        if not out.is_contiguous():
+            raise PB200Error("all_to_all needs a contiguous output tensor")
+        win.all_to_all_single(out, inp.contiguous(),
                               list(out_splits) if out_splits is not None and len(out_splits) else None,
                               list(in_splits) if in_splits is not None and len(in_splits) else None)
         return StreamOrderedWork(inp.device) if async_op else None
@@ -183,20 +188,23 @@ class B200CommsMixin:
             return work
 
     def all_to_all(self, collectiveArgs, retFlag=False, pair=False, pairIdx=0):
-        """list form (dist.all_to_all(list_out, list_in)): packed through the same push kernel"""
+        """list form (dist.all_to_all(list_out, list_in), pytorch_dist_backend.py:207-260): ONE push kernel
+        with per-destination source pointers and per-source landing offsets (pb200_a2a_list) — no cat
+        before, no split/copy after when the outputs live in the window"""
         ops_ = collectiveArgs.opTensor if not pair else collectiveArgs.opTensor_pair[pairIdx]
         ips_ = collectiveArgs.ipTensor if not pair else collectiveArgs.ipTensor_pair[pairIdx]
         if not isinstance(ips_, (list, tuple)):
             raise PB200Error("all_to_all expects lists of tensors")
-        flat_in = torch.cat([t.reshape(-1) for t in ips_])
-        flat_out = flat_in.new_empty(sum(t.numel() for t in ops_))
-        work = self._a2a(flat_out, flat_in, [t.numel() for t in ops_], [t.numel() for t in ips_],
-                         collectiveArgs.group, False)
-        off = 0
-        for t in ops_:
-            t.copy_(flat_out[off:off + t.numel()].view_as(t))
-            off += t.numel()
-        work = StreamOrderedWork(flat_in.device) if collectiveArgs.asyncOp else None
+        if not isinstance(ops_, (list, tuple)) or len(ops_) != len(ips_):
+            raise PB200Error("all_to_all expects output and input lists of world_size tensors")
+        group = collectiveArgs.group if collectiveArgs.group is not None else dist.group.WORLD
+        win = self._ensure_window(group)
+        # one push kernel: ips_[j] -> rank j, landing in that rank's ops_[me] (in place if it lives in
+        # the window, which is where alloc_empty puts comm buffers)
+        if any(not t.is_contiguous() for t in ops_):
+            raise PB200Error("all_to_all needs contiguous output tensors")
+        win.all_to_all(list(ops_), [t.contiguous() for t in ips_])
+        work = StreamOrderedWork(ips_[0].device) if collectiveArgs.asyncOp else None
         if collectiveArgs.asyncOp:
             collectiveArgs.waitObj.append(work)
         if retFlag:

@@ -123,8 +123,14 @@ class PeerWindow:
                 peers.append(buf)
                 ptrs.append(buf.data_ptr())
             else:
+                # the alias lives on the device ordinal the storage reports (the sender's), not on ours:
+                # set_() refuses to cross devices; the kernels only need the address, and peer access
+                # between the two ordinals is what makes it dereferenceable from this rank's GPU
                 st = torch.UntypedStorage._new_shared_cuda(*gathered[r])
-                t = torch.empty(0, dtype=torch.uint8, device=device).set_(st)
+                t = torch.empty(0, dtype=torch.uint8, device=st.device).set_(st)
+                if st.device != device and st.device.type == "cuda":
+                    if not torch.cuda.can_device_access_peer(device.index, st.device.index):
+                        raise PB200Error(f"no peer access from {device} to {st.device}")
                 peers.append(t)
                 ptrs.append(t.data_ptr())
         dist.barrier(group)
@@ -190,46 +196,84 @@ class PeerWindow:
     def _stream(self, stream) -> int:
         return (stream or torch.cuda.current_stream(self.device)).cuda_stream
 
+    def _staging_offset(self, nbytes: int) -> int:
+        """Where a result that has no home in the window is staged: the TOP of the window, growing
+        downwards, never overlapping what the bump allocator has handed out (live comm buffers grow
+        upwards from 0).  Raises instead of overwriting a live tensor."""
+        off = (self.window_bytes - int(nbytes)) // _ALIGN * _ALIGN
+        if off < self._bump:
+            raise PB200Error(
+                f"all-to-all result of {nbytes} B does not fit the peer window beside the {self._bump} B of "
+                f"buffers allocated in it (window {self.window_bytes} B): allocate the output with "
+                "alloc()/alloc_empty so that peers write it in place, or size the window up front "
+                "(PB200_WINDOW_BYTES)")
+        return off
+
+    @staticmethod
+    def _dim0_elems(t: torch.Tensor, splits):
+        """c10d splits count rows along dim 0; the kernel takes elements of the flattened tensor."""
+        if t.dim() <= 1 or t.shape[0] == 0:
+            return [int(v) for v in splits]
+        row = t.numel() // t.shape[0]
+        return [int(v) * row for v in splits]
+
     def all_to_all_single(self, out: Optional[torch.Tensor], inp: torch.Tensor,
                           out_splits: Optional[Sequence[int]] = None,
                           in_splits: Optional[Sequence[int]] = None,
                           out_window_off: Optional[int] = None, stream=None) -> torch.Tensor:
-        """c10d all_to_all_single semantics (splits in ELEMENTS of inp.dtype).  If `out` already
-        lives inside the window the peers write it in place (zero copy); otherwise the result is
-        staged at out_window_off (default 0) and copied into `out` on the stream."""
+        """c10d all_to_all_single semantics (splits along dim 0, as c10d counts them).  If `out`
+        already lives inside the window the peers write it in place (zero copy); otherwise the result is
+        staged — at out_window_off if the caller carved the window itself, else at the top of the
+        window, clear of every tensor alloc() has handed out — and copied into `out` on the stream.
+        With out=None the staged view is returned; it is valid until the next staged call."""
         if not inp.is_cuda or not inp.is_contiguous():
             raise PB200Error("all_to_all_single needs a contiguous CUDA input")
         es = inp.element_size()
         W = self.world
-        if (out_splits is None or len(out_splits) == 0) != (in_splits is None or len(in_splits) == 0):
+        have_in = in_splits is not None and len(in_splits) > 0
+        have_out = out_splits is not None and len(out_splits) > 0
+        if have_in:
+            in_splits = self._dim0_elems(inp, in_splits)
+        if have_out:
+            out_splits = self._dim0_elems(out if out is not None else inp, out_splits)
+        if have_in != have_out:
             # c10d allows giving only one side; the missing side is the equal split
             n_in, n_out = inp.numel(), (out.numel() if out is not None else inp.numel())
-            in_splits = list(in_splits) if in_splits else [n_in // W] * W
-            out_splits = list(out_splits) if out_splits else [n_out // W] * W
+            if (not have_in and n_in % W) or (not have_out and n_out % W):
+                raise PB200Error("equal-split side of all_to_all_single needs numel % world_size == 0")
+            in_splits = list(in_splits) if have_in else [n_in // W] * W
+            out_splits = list(out_splits) if have_out else [n_out // W] * W
+            have_in = have_out = True
+        if have_in:
+            if len(in_splits) != W or len(out_splits) != W:
+                raise PB200Error("split lists must have world_size entries")
+            if sum(in_splits) != inp.numel():
+                raise PB200Error(f"input splits sum to {sum(in_splits)} elements, the input has {inp.numel()}")
+            total_out = sum(out_splits)
+        else:
+            if inp.numel() % W:
+                raise PB200Error("equal-split all_to_all_single needs numel % world_size == 0")
+            total_out = inp.numel()
         copy_out = None
         if out is not None:
             if out.dtype != inp.dtype or not out.is_contiguous():
                 raise PB200Error("out must be contiguous with the input dtype")
+            if out.numel() < total_out:
+                raise PB200Error(f"out has {out.numel()} elements, the splits deliver {total_out}")
             off = self.offset_of(out)
             if off is not None:
                 out_window_off = off
             else:
                 copy_out = out
-                out_window_off = 0 if out_window_off is None else out_window_off
-        elif out_window_off is None:
-            out_window_off = 0
+        if out_window_off is None:
+            out_window_off = self._staging_offset(total_out * es)
+        if out_window_off + total_out * es > self.window_bytes:
+            raise PB200Error("all-to-all result does not fit the window at the requested offset")
         lib = _cabi.load()
-        if in_splits:
-            if len(in_splits) != W or len(out_splits) != W:
-                raise PB200Error("split lists must have world_size entries")
-            isb = _cabi.i64_array([int(s) * es for s in in_splits])
-            osb = _cabi.i64_array([int(s) * es for s in out_splits])
-            total_out = sum(int(s) for s in out_splits)
-        else:
-            if inp.numel() % W:
-                raise PB200Error("equal-split all_to_all_single needs numel % world_size == 0")
-            isb = osb = None
-            total_out = inp.numel()
+        isb = osb = None
+        if have_in:
+            isb = _cabi.i64_array([s_ * es for s_ in in_splits])
+            osb = _cabi.i64_array([s_ * es for s_ in out_splits])
         rc = lib.pb200_a2a_single(self._comm, inp.data_ptr(), inp.numel() * es, isb, osb,
                                   int(out_window_off), None if copy_out is None else copy_out.data_ptr(),
                                   self._stream(stream))
@@ -237,6 +281,38 @@ class PeerWindow:
         if out is not None:
             return out
         return self.view(out_window_off, total_out, inp.dtype)
+
+    def all_to_all(self, outs: Sequence[torch.Tensor], ins: Sequence[torch.Tensor], stream=None) -> None:
+        """dist.all_to_all(output_tensor_list, input_tensor_list): ins[j] goes to rank j, outs[r] receives
+        from rank r (pb200_a2a_list).  Output tensors that live in the window are written in place by
+        the peers; the others are staged at the top of the window and copied out on the stream.  No
+        cat before, no split after."""
+        W = self.world
+        if len(outs) != W or len(ins) != W:
+            raise PB200Error("all_to_all needs world_size input and output tensors")
+        for t in list(outs) + list(ins):
+            if not t.is_cuda or not t.is_contiguous():
+                raise PB200Error("all_to_all needs contiguous CUDA tensors")
+        nb_out = [t.numel() * t.element_size() for t in outs]
+        offs, copies = [], []
+        staged = sum((b + _ALIGN - 1) // _ALIGN * _ALIGN for t, b in zip(outs, nb_out) if self.offset_of(t) is None)
+        cursor = self._staging_offset(staged) if staged else 0
+        for t, b in zip(outs, nb_out):
+            off = self.offset_of(t)
+            if off is None:
+                off = cursor
+                cursor += (b + _ALIGN - 1) // _ALIGN * _ALIGN
+                copies.append(t.data_ptr())
+            else:
+                copies.append(None)
+            offs.append(off)
+        in_ptrs = (C.c_void_p * W)(*[t.data_ptr() if t.numel() else None for t in ins])
+        out_copy = (C.c_void_p * W)(*copies) if any(c is not None for c in copies) else None
+        rc = _cabi.load().pb200_a2a_list(self._comm, in_ptrs,
+                                         _cabi.i64_array([t.numel() * t.element_size() for t in ins]),
+                                         _cabi.i64_array(offs), _cabi.i64_array(nb_out), out_copy,
+                                         self._stream(stream))
+        _cabi.check(rc, "pb200_a2a_list")
 
     def pooled_forward(self, pooled: torch.Tensor, batch_split: Sequence[int],
                        tables_split: Sequence[int], emb_dim: int, layout: str = "BTD",

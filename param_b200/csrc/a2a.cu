@@ -469,6 +469,39 @@ extern "C" int pb200_a2a_single(pb200_a2a_comm *c, const void *in, int64_t total
     return PB200_OK;
 }
 
+// List form (dist.all_to_all(output_tensor_list, input_tensor_list)): W separate input blocks, W separate
+// landing places.  Same kernel, same protocol: the per-destination source pointer and the per-source
+// receive offset were already independent — nothing is packed before or unpacked after.
+extern "C" int pb200_a2a_list(pb200_a2a_comm *c, const void *const *in_ptrs, const int64_t *in_bytes,
+                              const int64_t *out_window_offs, const int64_t *out_bytes,
+                              void *const *out_copy, void *stream) {
+    if (!c || !in_ptrs || !in_bytes || !out_window_offs || !out_bytes) return PB200_EINVAL;
+    const int W = c->world;
+    A2AArgs a{};
+    long long max_peer = 0;
+    for (int r = 0; r < W; ++r) {
+        if (in_bytes[r] < 0 || out_bytes[r] < 0 || out_window_offs[r] < 0) return PB200_EINVAL;
+        if (in_bytes[r] > 0 && !in_ptrs[r]) return PB200_EINVAL;
+        if (out_window_offs[r] + out_bytes[r] > c->window_bytes) return PB200_EINVAL;
+        a.copy[r].src = (const unsigned char *)in_ptrs[r];
+        a.copy[r].src_stride = 0;
+        a.copy[r].dst_stride = 0;
+        a.copy[r].run_bytes = in_bytes[r];
+        a.copy[r].rows = in_bytes[r] > 0 ? 1 : 0;
+        a.recv_off[r] = out_window_offs[r];
+        if (in_bytes[r] > max_peer) max_peer = in_bytes[r];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = a2a_launch_args(c, a, max_peer, st);
+    if (rc != PB200_OK) return rc;
+    if (out_copy)
+        for (int r = 0; r < W; ++r)
+            if (out_copy[r] && out_bytes[r] > 0)
+                PB200_CUDA_TRY(cudaMemcpyAsync(out_copy[r], c->peer_data[c->rank] + out_window_offs[r],
+                                               (size_t)out_bytes[r], cudaMemcpyDeviceToDevice, st));
+    return PB200_OK;
+}
+
 extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t in_stride_t,
                                     int64_t in_stride_n, int32_t emb_dim,
                                     const int64_t *batch_split, const int64_t *tables_split,

@@ -226,3 +226,84 @@ def test_sparse_data_dist_slot_overflow_is_reported(cuda_device):
             w.sparse_data_dist(lens[r], idx[r], [1, 1], b, 0, 4096, slot, stream=st)
     torch.cuda.synchronize()
     assert all(w.error() == 2 for w in grp.windows)
+
+
+@pytest.mark.parametrize("W", [2, 4])
+def test_staged_output_never_lands_on_live_window_tensors(cuda_device, oracle, W):
+    """an output that lives outside the window used to be staged at window offset 0,
+    on top of the comm buffers the bump allocator hands out from there.  Now it is staged at the top of
+    the window: the live in-window tensors (here: the INPUT of the very same collective) are intact
+    after several iterations, and a result that cannot fit beside them raises instead of overwriting."""
+    from param_b200._cabi import PB200Error
+    grp = _group(W, 1 << 20, cuda_device)
+    n = 8192
+    rng = np.random.default_rng(W)
+    ins_h = [rng.integers(0, 1 << 20, size=n).astype(np.int64) for _ in range(W)]
+    ins = []
+    for r, w in enumerate(grp.windows):
+        t, off = w.alloc(n, torch.int64)        # what alloc_random does for ipTensor: offset 0 of the window
+        assert off == 0
+        t.copy_(torch.from_numpy(ins_h[r]))
+        ins.append(t)
+    splits = rng.integers(1, 40, size=(W, W))
+    splits[:, :] = splits * (n // splits.sum(axis=1, keepdims=True).max() // 2)
+    for r in range(W):
+        splits[r, -1] += n - splits[r].sum()
+    want = oracle.all_to_all_single(ins_h, splits)
+    outs = [torch.empty(int(splits[:, r].sum()), dtype=torch.int64, device=cuda_device) for r in range(W)]
+    for _ in range(3):      # iteration 2 used to re-send what iteration 1 had received
+        _run_all(grp, lambda r, w, st: w.all_to_all_single(
+            outs[r], ins[r], [int(splits[s][r]) for s in range(W)], [int(x) for x in splits[r]], stream=st))
+        for r in range(W):
+            assert np.array_equal(outs[r].cpu().numpy(), want[r])
+            assert np.array_equal(ins[r].cpu().numpy(), ins_h[r]), "the live input buffer was overwritten"
+    # no room left beside the live buffers: refuse
+    for w in grp.windows:
+        w.alloc((1 << 20) // 8 - n - 64, torch.int64)
+    with pytest.raises(PB200Error):
+        grp.windows[0].all_to_all_single(outs[0], ins[0], [int(splits[s][0]) for s in range(W)],
+                                         [int(x) for x in splits[0]])
+
+
+@pytest.mark.parametrize("W", [2, 3, 8])
+@pytest.mark.parametrize("in_window", [False, True])
+def test_list_form_all_to_all(cuda_device, W, in_window):
+    """dist.all_to_all(output_tensor_list, input_tensor_list) (pytorch_dist_backend.py:207-260) as ONE push
+    kernel with per-destination sources and per-source landing places: ragged block sizes, outputs
+    inside the window (written in place by the peers) or outside (staged + copied out)."""
+    grp = _group(W, 1 << 20, cuda_device)
+    rng = np.random.default_rng(W + 50)
+    sizes = rng.integers(0, 500, size=(W, W))          # sizes[s][d]: elements rank s sends to rank d
+    sizes[0, W - 1] = 0
+    ins = [[(torch.arange(int(sizes[s][d]), dtype=torch.float32, device=cuda_device) + 1000 * s + 10 * d)
+            for d in range(W)] for s in range(W)]
+    outs = []
+    for r, w in enumerate(grp.windows):
+        if in_window:
+            w.alloc(77, torch.float32)                  # something live at offset 0
+            outs.append([w.alloc(int(sizes[s][r]), torch.float32)[0] for s in range(W)])
+        else:
+            outs.append([torch.empty(int(sizes[s][r]), dtype=torch.float32, device=cuda_device) for s in range(W)])
+    for _ in range(2):
+        _run_all(grp, lambda r, w, st: w.all_to_all(outs[r], ins[r], stream=st))
+        for r in range(W):
+            for s in range(W):
+                assert torch.equal(outs[r][s], ins[s][r]), (r, s)
+
+
+def test_all_to_all_single_counts_splits_along_dim0(cuda_device, oracle):
+    """c10d counts split sizes in rows of dim 0: a [rows, 6] tensor with splits in rows"""
+    W = 2
+    grp = _group(W, 1 << 18, cuda_device)
+    rows = np.array([[3, 5], [2, 7]])
+    ins_h = [np.arange(rows[r].sum() * 6, dtype=np.float32).reshape(-1, 6) + 100 * r for r in range(W)]
+    want = oracle.all_to_all_single([x.reshape(-1) for x in ins_h], rows * 6)
+    ins = [torch.from_numpy(x).to(cuda_device) for x in ins_h]
+    outs = [torch.empty((int(rows[:, r].sum()), 6), device=cuda_device) for r in range(W)]
+    _run_all(grp, lambda r, w, st: w.all_to_all_single(
+        outs[r], ins[r], [int(rows[s][r]) for s in range(W)], [int(x) for x in rows[r]], stream=st))
+    for r in range(W):
+        assert np.array_equal(outs[r].cpu().numpy().reshape(-1), want[r])
+    from param_b200._cabi import PB200Error
+    with pytest.raises(PB200Error):     # output too small for what the splits deliver
+        grp.windows[0].all_to_all_single(torch.empty((2, 6), device=cuda_device), ins[0], [3, 2], [3, 5])
