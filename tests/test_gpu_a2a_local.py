@@ -245,10 +245,10 @@ def test_staged_output_never_lands_on_live_window_tensors(cuda_device, oracle, W
         assert off == 0
         t.copy_(torch.from_numpy(ins_h[r]))
         ins.append(t)
-    splits = rng.integers(1, 40, size=(W, W))
-    splits[:, :] = splits * (n // splits.sum(axis=1, keepdims=True).max() // 2)
-    for r in range(W):
-        splits[r, -1] += n - splits[r].sum()
+    splits = np.zeros((W, W), np.int64)
+    for r in range(W):          # every rank sends all n elements, cut at random places
+        cuts = np.sort(rng.choice(np.arange(1, n), size=W - 1, replace=False))
+        splits[r] = np.diff(np.concatenate([[0], cuts, [n]]))
     want = oracle.all_to_all_single(ins_h, splits)
     outs = [torch.empty(int(splits[:, r].sum()), dtype=torch.int64, device=cuda_device) for r in range(W)]
     for _ in range(3):      # iteration 2 used to re-send what iteration 1 had received
