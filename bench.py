@@ -51,6 +51,11 @@ def parse_args(argv=None):
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--e2e-group", type=int, default=16, help="tables per H2D/kernel/D2H pipeline group")
+    ap.add_argument("--presort", choices=["side", "inline"], default="inline",
+                    help="where the backward's sort plan is built: after the forward on the same stream, or "
+                         "on a side stream queued before the forward (inside the timed step either way)")
+    ap.add_argument("--skip-uniform", action="store_true", help="skip the alpha=0 roofline leg")
+    ap.add_argument("--quick", action="store_true", help="skip the alternative kernel variants")
     return ap.parse_args(argv)
 
 
@@ -142,10 +147,10 @@ def ev_time(fn, iters, stream=None):
 # ------------------------------------------------------------------------------------------------
 def build_workload(args, dev):
     from param_b200 import ops
-    from param_b200.compute.pt.pytorch_emb import zipf_cdf
     T, B, L, D = args.tables, args.batch, args.bag, args.dim
     free, total = torch.cuda.mem_get_info(dev)
-    fixed = T * B * L * 8 + (T * B + 1) * 8 + 2 * T * B * D * 4 + (6 << 30)  # idx, off, out, grad, slack
+    # idx, off, out, a gradient copy for the parity check, the sort plan (24 B per lookup + histograms), slack
+    fixed = T * B * L * 8 + (T * B + 1) * 8 + 2 * T * B * D * 4 + T * B * L * 28 + (6 << 30)
     rows = args.rows
     max_rows = int((free - fixed) // (T * D * 4))
     scaled = False
@@ -154,15 +159,69 @@ def build_workload(args, dev):
     arena = ops.TableArena.allocate([rows] * T, D, dev)
     ops.fill_uniform_(arena.weights, -(1.0 / rows) ** 0.5, (1.0 / rows) ** 0.5, seed=2026)
     idx = torch.empty(T * B * L, dtype=torch.int64, device=dev)
-    if args.alpha > 0:
-        cdf = torch.from_numpy(zipf_cdf(args.alpha, rows)).to(dev)
-    else:
-        cdf = torch.linspace(1.0 / rows, 1.0, rows, dtype=torch.float64, device=dev)
-    for t in range(T):
-        ops.fill_zipf_indices_(idx[t * B * L:(t + 1) * B * L], L, cdf, seed=1000 + t, dedupe=args.alpha > 0)
+    fill_indices(args, idx, rows, args.alpha, dev)
     off = torch.arange(T * B + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
     return arena, idx, off, rows, scaled
+
+
+def fill_indices(args, idx, rows, alpha, dev):
+    """(re)generate the request in place: Zipf(alpha) by inverse CDF, per-bag distinct like the reference's
+    init_indices (pytorch_emb.py:138-160), or uniform for alpha == 0"""
+    from param_b200 import ops
+    from param_b200.compute.pt.pytorch_emb import zipf_cdf
+    T, B, L = args.tables, args.batch, args.bag
+    if alpha > 0:
+        cdf = torch.from_numpy(zipf_cdf(alpha, rows)).to(dev)
+    else:
+        cdf = torch.linspace(1.0 / rows, 1.0, rows, dtype=torch.float64, device=dev)
+    for t in range(T):
+        ops.fill_zipf_indices_(idx[t * B * L:(t + 1) * B * L], L, cdf, seed=1000 + t, dedupe=alpha > 0)
+    torch.cuda.synchronize()
+
+
+def sampled_parity(args, arena, idx, off, out, rows, n_samples=64):
+    """CHECKER (the one place besides cpu_baseline where bench.py touches oracle/): after the timed region,
+    one more forward + backward of the SAME kernels on the same request; 64 sampled bags of the pooled
+    output are compared bit for bit with the CPU oracle (fp32 sum in index order over the rows as they are
+    in HBM), and the update of 64 sampled rows with a float64 sum over ALL their lookups (1e-5 relative)."""
+    import numpy as np
+    from oracle import oracle
+    from param_b200 import ops
+    T, B, L, D = args.tables, args.batch, args.bag, args.dim
+    rng = np.random.default_rng(12345)
+    ts, bs = rng.integers(0, T, n_samples), rng.integers(0, B, n_samples)
+    ops.tbe_forward(arena, idx, off, B, layout="BTD", algo=args.fwd_algo, out=out)
+    torch.cuda.synchronize()
+    ok_fwd = True
+    for t, b in zip(ts.tolist(), bs.tolist()):
+        ids = idx[(t * B + b) * L:(t * B + b + 1) * L]
+        w = arena.weights[t * rows + ids].cpu().numpy()
+        want = oracle.embbag_fwd(w, np.arange(L, dtype=np.int64), np.zeros(1, np.int64))[0]
+        got = out[b, t * D:(t + 1) * D].cpu().numpy()
+        ok_fwd &= bool(np.array_equal(got, want))
+    # backward: the rows of the first lookup of each sampled bag; every lookup of such a row is found by
+    # scanning its table's indices.  The check step uses lr = 1 so that the update is not below the fp32
+    # resolution of the weights (it runs after the timed region).
+    lr = 1.0
+    sample_rows = sorted({(int(t), int(idx[(int(t) * B + int(b)) * L].item())) for t, b in zip(ts, bs)})
+    before = {tr: arena.weights[tr[0] * rows + tr[1]].double().cpu().numpy() for tr in sample_rows}
+    grad = out.clone()
+    ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, grad, layout="BTD", scale=-lr,
+                     algo="sorted", max_table_rows=rows)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (t, r) in sample_rows:
+        pos = (idx[t * B * L:(t + 1) * B * L] == r).nonzero().view(-1)
+        bags = torch.div(pos, L, rounding_mode="floor")
+        g = grad[bags, t * D:(t + 1) * D].double().sum(dim=0).cpu().numpy()
+        want = before[(t, r)] - lr * g
+        got = arena.weights[t * rows + r].double().cpu().numpy()
+        worst = max(worst, float(np.abs(got - want).max()) / max(float(np.abs(want).max()), 1e-30))
+    del grad
+    return {"parity_sampled": bool(ok_fwd and worst <= 1e-5), "fwd_bags_bit_exact": bool(ok_fwd),
+            "bwd_rows_max_rel_err": worst, "bags": int(n_samples), "rows": len(sample_rows),
+            "checker": "oracle/param_oracle.c embbag_fwd (bit-exact) + float64 sum over all lookups of the row (1e-5)"}
 
 
 def run_b200(args):
@@ -180,18 +239,43 @@ def run_b200(args):
     out = torch.empty((B, T * D), dtype=torch.float32, device=dev)
     lookups = T * B * L
     bwd_algo = "sorted" if args.bwd_algo == "auto" else args.bwd_algo
+    side = torch.cuda.Stream(device=dev)
+    plans = {}
 
     def fwd():
         ops.tbe_forward(arena, idx, off, B, layout="BTD", algo=args.fwd_algo, out=out)
 
-    def bwd():
+    def plan(stream=None, exact=False):
+        # the index-only half of the backward: every table's lookups sorted by row (hand-written radix sort)
+        key = "exact" if exact else "sorted"
+        p = ops.tbe_plan(arena.row_offsets, T, D, idx, off, B, rows, layout="BTD", exact=exact, stream=stream,
+                         buf=plans.get(key))
+        plans[key] = p.buf
+        return p
+
+    def reduce(p):
         # the pooled output doubles as the incoming gradient (same shape; saves 8.6 GB of HBM)
         ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, layout="BTD",
-                         scale=-args.lr, algo=bwd_algo)
+                         scale=-args.lr, algo=bwd_algo, max_table_rows=rows, plan=p)
+
+    def bwd():
+        if bwd_algo == "atomic":
+            ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, layout="BTD",
+                             scale=-args.lr, algo="atomic")
+        else:
+            reduce(plan(exact=bwd_algo == "exact"))
 
     def step():
-        fwd()
-        bwd()
+        # one training step of the path: forward over all tables, then the backward (sort plan + segmented
+        # reduce, fused SGD into the arena).  --presort side queues the sort on a side stream before the
+        # forward (it needs the indices only); the timed region contains it either way.
+        if args.presort == "side" and bwd_algo != "atomic":
+            p = plan(stream=side, exact=bwd_algo == "exact")
+            fwd()
+            reduce(p)
+        else:
+            fwd()
+            bwd()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -210,41 +294,10 @@ def run_b200(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_step = float(tmax.item())
         dist.barrier()
-    # per-kernel durations for the roofline (same process, CUDA events on the launching stream)
-    ms_fwd = ev_time(fwd, args.steps)
-    ms_bwd = ev_time(bwd, args.steps)
-    ms_fwd_direct = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="direct", out=out), args.steps)
-    ms_fwd_staged = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="staged", out=out), args.steps)
-    ms_fwd_pipe = ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="pipelined", out=out), args.steps)
-    ms_bwd_other = None
-    other = "atomic" if bwd_algo == "sorted" else "sorted"
-    try:
-        ms_bwd_other = ev_time(lambda: ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
-                                                        layout="BTD", scale=-args.lr, algo=other),
-                               max(2, args.steps // 2))
-    except Exception as exc:  # noqa: BLE001
-        ms_bwd_other = f"failed: {exc}"
-
-    # the fused-optimizer backward (one deterministic update per touched row, C ABI §3b): exact SGD and
-    # fbgemm's default exact rowwise Adagrad (what comms_utils.py:2015 asks for)
-    ms_bwd_exact = ms_bwd_adagrad = None
-    try:
-        ms_bwd_exact = ev_time(lambda: ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
-                                                              optimizer="exact_sgd", lr=args.lr), max(2, args.steps // 2))
-        state = torch.zeros(arena.total_rows, dtype=torch.float32, device=dev)
-        ms_bwd_adagrad = ev_time(lambda: ops.tbe_backward_fused(arena.weights, arena.row_offsets, T, D, idx, off, B,
-                                                                out, optimizer="exact_row_wise_adagrad", lr=args.lr,
-                                                                state=state), max(2, args.steps // 2))
-        del state
-    except Exception as exc:  # noqa: BLE001
-        ms_bwd_exact = ms_bwd_exact if ms_bwd_exact is not None else f"failed: {exc}"
-        ms_bwd_adagrad = f"failed: {exc}"
+    parity = sampled_parity(args, arena, idx, off, out, rows) if rank == 0 else None
 
     peak, peak_src = measured_peaks()
     fwd_bytes, bwd_bytes = algorithmic_bytes(T, B, L, D)
-    # `roofline` is quoted for the forward lookup kernel: ONE launch per step, the kernel north_star's
-    # 70 %-of-HBM target names.  The backward is a pipeline of several kernels (pair build, library
-    # radix sort, segmented reduce) and is reported as a whole in `roofline_bwd`.
     traffic = {}
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -253,10 +306,66 @@ def run_b200(args):
         except Exception:
             traffic = {}
 
-    def roof(nbytes, ms):
+    def roof(nbytes, ms, dram=None):
         a = nbytes / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(a / peak, 4), "peak_source": peak_src}
+        r = {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
+             "peak_source": peak_src, "algorithmic_bytes": int(nbytes), "ms": round(ms, 4), "traffic": dram,
+             "traffic_source": None if dram is None else
+             "static: ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch at this size "
+             "(profiles/traffic.json), not measured in this run"}
+        if dram is not None:
+            r["dram_gbs"] = round(dram / (ms * 1e-3) / 1e9, 1)
+            r["frac_dram"] = round(dram / (ms * 1e-3) / 1e9 / peak, 4)
+        return r
+
+    def legs(tag):
+        """CUDA-event time of every kernel (group) of the step, same process, same inputs"""
+        k = {}
+        k["fwd"] = ev_time(fwd, args.steps)
+        if bwd_algo != "atomic":
+            k["sort_plan"] = ev_time(lambda: plan(exact=bwd_algo == "exact"), args.steps)
+            p = plan(exact=bwd_algo == "exact")
+            k["reduce"] = ev_time(lambda: reduce(p), args.steps)
+        k["bwd"] = ev_time(bwd, args.steps)
+        sfx = "" if tag == "zipf" else "_uniform"
+        r = {"fwd": dict(roof(fwd_bytes, k["fwd"], traffic.get("fwd" + sfx)),
+                         kernel="tbe_fwd_direct_kernel (1 launch/step)",
+                         lookups_per_s=lookups / k["fwd"] * 1e3,
+                         param_bw_gbs=round(lookups * D * 4 / k["fwd"] / 1e6, 1))}
+        if "reduce" in k:
+            r["bwd_reduce"] = dict(roof(bwd_bytes, k["reduce"], traffic.get("bwd_reduce" + sfx)),
+                                   kernel="segment_reduce_kernel (1 launch/step; carries all of the backward's "
+                                          "algorithmic bytes: gradient rows in, row read-modify-write)")
+            sort_bytes = lookups * 48
+            r["bwd_sort_plan"] = dict(roof(sort_bytes, k["sort_plan"], traffic.get("bwd_sort_plan" + sfx)),
+                                      kernel="radix_hist/scan/scatter_kernel x passes (6 launches/step at 20 key bits)",
+                                      keys_per_s=lookups / k["sort_plan"] * 1e3,
+                                      note="48 B per lookup moved by a 2-pass plan (csrc/radix_sort.cu); overhead on "
+                                           "top of the backward's algorithmic bytes, which are charged to bwd_reduce")
+        r["bwd"] = dict(roof(bwd_bytes, k["bwd"], traffic.get("bwd" + sfx)), kernel="backward as a whole", algo=bwd_algo)
+        return k, r
+
+    ms, roofs = legs("zipf" if args.alpha > 0 else "uniform")
+    # the single kernel that takes the largest share of the step
+    dom = "bwd_reduce" if ("bwd_reduce" in roofs and ms["reduce"] >= ms["fwd"]) else "fwd"
+    extra = {}
+    if not args.quick:
+        extra["fwd_staged_ms"] = round(ev_time(lambda: ops.tbe_forward(arena, idx, off, B, algo="staged", out=out), args.steps), 4)
+        try:
+            n2 = max(2, args.steps // 2)
+            extra["bwd_atomic_ms"] = round(ev_time(lambda: ops.tbe_backward(
+                arena.weights, arena.row_offsets, T, D, idx, off, B, out, layout="BTD", scale=-args.lr,
+                algo="atomic"), n2), 4)
+            extra["bwd_exact_sgd_ms"] = round(ev_time(lambda: ops.tbe_backward_fused(
+                arena.weights, arena.row_offsets, T, D, idx, off, B, out, optimizer="exact_sgd", lr=args.lr,
+                max_table_rows=rows), n2), 4)
+            state = torch.zeros(arena.total_rows, dtype=torch.float32, device=dev)
+            extra["bwd_exact_rowwise_adagrad_ms"] = round(ev_time(lambda: ops.tbe_backward_fused(
+                arena.weights, arena.row_offsets, T, D, idx, off, B, out, optimizer="exact_row_wise_adagrad",
+                lr=args.lr, state=state, max_table_rows=rows), n2), 4)
+            del state
+        except Exception as exc:  # noqa: BLE001
+            extra["variants_failed"] = str(exc)
 
     res = {
         "metric": METRIC, "value": world * lookups / (ms_step * 1e-3), "unit": UNIT,
@@ -267,34 +376,35 @@ def run_b200(args):
                                f"(scaled from 10M rows to fit 180 GB HBM{'; further scaled to free memory' if scaled else ''}), "
                                f"global batch {B}, bag {L}, Zipf alpha={args.alpha}, int64 indices",
                    "tables": T, "rows_per_table": rows, "dim": D, "batch": B, "bag": L, "alpha": args.alpha,
-                   "fwd_algo": args.fwd_algo, "bwd_algo": bwd_algo,
+                   "fwd_algo": args.fwd_algo, "bwd_algo": bwd_algo, "presort": args.presort,
                    "l2_policy": "inputs larger than L2 (arena %.1f GB, pooled output %.1f GB)" %
                                 (arena.weights.numel() * 4 / 1e9, out.numel() * 4 / 1e9),
                    "parallelism": "replicas" if world > 1 else "single"},
         "gpu_launches": int(launches),
-        "roofline": dict(roof(fwd_bytes, ms_fwd), kernel="tbe_fwd_direct_kernel (forward lookup, 1 launch/step)",
-                         traffic=traffic.get("fwd") if abs(args.alpha - 1.15) < 1e-9 else traffic.get("fwd_uniform"),
-                         algorithmic_bytes=fwd_bytes, ms=round(ms_fwd, 4),
-                         note="Zipf skew: most row reads hit L1/L2, so algorithmic GB/s exceeds the DRAM peak; "
-                              "see roofline_uniform / profiles/ for the HBM-bound case" if args.alpha > 0 else
-                              "uniform indices: HBM-bound"),
-        "roofline_bwd": dict(roof(bwd_bytes, ms_bwd), kernel="backward pipeline (build_pairs + radix sort + segment_reduce)"
-                             if bwd_algo == "sorted" else "tbe_bwd_atomic_kernel",
-                             traffic=traffic.get("bwd"), algorithmic_bytes=bwd_bytes, ms=round(ms_bwd, 4)),
-        "kernels": {"fwd": dict(roof(fwd_bytes, ms_fwd), ms=round(ms_fwd, 4), lookups_per_s=lookups / ms_fwd * 1e3,
-                                param_bw_gbs=round(lookups * D * 4 / ms_fwd / 1e6, 1)),
-                    "fwd_direct_ms": round(ms_fwd_direct, 4), "fwd_staged_ms": round(ms_fwd_staged, 4), "fwd_pipelined_ms": round(ms_fwd_pipe, 4),
-                    "bwd": dict(roof(bwd_bytes, ms_bwd), ms=round(ms_bwd, 4), algo=bwd_algo),
-                    f"bwd_{other}_ms": ms_bwd_other if isinstance(ms_bwd_other, str) else round(ms_bwd_other, 4),
-                    "bwd_exact_sgd_ms": ms_bwd_exact if not isinstance(ms_bwd_exact, float) else round(ms_bwd_exact, 4),
-                    "bwd_exact_rowwise_adagrad_ms": ms_bwd_adagrad if not isinstance(ms_bwd_adagrad, float)
-                    else round(ms_bwd_adagrad, 4)},
+        "roofline": dict(roofs[dom], dominant_kernel=dom,
+                         share_of_step=round((ms["reduce"] if dom == "bwd_reduce" else ms["fwd"]) / ms_step, 3),
+                         note="Zipf skew: most row reads hit L1/L2, so algorithmic GB/s can exceed the DRAM peak; "
+                              "frac_dram is the DRAM-traffic figure and roofline_uniform the HBM-bound case"
+                              if args.alpha > 0 else "uniform indices: HBM-bound"),
+        "roofline_kernels": roofs,
+        "kernels_ms": dict({k: round(v, 4) for k, v in ms.items()}, **extra),
+        "parity": parity,
         "clocks": clk.summary(),
     }
     if rank == 0 and not args.skip_e2e:
         res["e2e"] = run_e2e(args, arena, idx, off, lookups)
     if rank == 0 and world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_baseline(args, arena, idx, rows, backward=True)
+    if rank == 0 and world == 1 and args.alpha > 0 and not args.skip_uniform:
+        # the HBM-bound leg: the same arena and kernels under uniform indices (no cache help), timed in
+        # this run.  Last, because it overwrites the request.
+        fill_indices(args, idx, rows, 0.0, dev)
+        ms_u, roofs_u = legs("uniform")
+        ms_step_u = ev_time(step, max(3, args.steps // 2))
+        res["roofline_uniform"] = dict(roofs_u, kernels_ms={k: round(v, 4) for k, v in ms_u.items()},
+                                       ms_per_step=round(ms_step_u, 4), value=lookups / (ms_step_u * 1e-3),
+                                       note="alpha = 0 on the same arena: every row read misses the caches, "
+                                            "DRAM traffic ~ algorithmic bytes")
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

@@ -36,9 +36,9 @@
 
 namespace pb200 {
 
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 16;                                  // lookups per thread per sub-tile
+constexpr int kSortItems = 8;                                   // lookups per thread per sub-tile
 constexpr int kSortSub = kSortThreads * kSortItems;             // 4096 lookups per sub-tile
 
 struct SortArgs {
@@ -81,6 +81,23 @@ __device__ __forceinline__ void tile_range(const SortArgs &a, int t, int tile, l
     p1 = (long long)off[tb0 + b1];
 }
 
+// Lanes of the warp that hold the same digit as this lane (only lanes with valid == true count).
+// One vote.ballot per digit bit — ~4 issue slots per bit, spread over the four schedulers of an SM.  The
+// hardware match.any did the same in one instruction but runs on the ADU pipe at ~2 cycles per lane: the
+// first version of these kernels was ADU-bound (95 % busy in the histogram, profiles/r02b_*.md).
+__device__ __forceinline__ unsigned digit_peers(unsigned d, bool valid, int bits) {
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < kSortMaxDigit; ++b) {
+        if (b < bits) {                                   // warp-uniform
+            const bool bit = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+    }
+    return peers;
+}
+
 // ---- K1: digit histogram of one tile ---------------------------------------------------------------
 template <typename index_t, bool FIRST>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const SortArgs a) {
@@ -103,19 +120,21 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const SortArgs
     constexpr int U = 4;
     for (long long base = p0; base < p1; base += (long long)kSortThreads * U) {   // CTA-uniform trip count
         unsigned d[U];
+        bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long pos = base + (long long)u * kSortThreads + threadIdx.x;
-            d[u] = 0xffffffffu;
-            if (pos < p1) {
+            ok[u] = pos < p1;
+            d[u] = 0;
+            if (ok[u]) {
                 const unsigned key = FIRST ? (unsigned)ld_index<index_t>(idx + pos) : a.src[pos - origin].x;
                 d[u] = (key >> a.shift) & mask;
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const unsigned peers = __match_any_sync(0xffffffffu, d[u]);
-            if (d[u] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d[u]], (unsigned)__popc(peers));
+            const unsigned peers = digit_peers(d[u], ok[u], a.bits);
+            if (ok[u] && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d[u]], (unsigned)__popc(peers));
         }
     }
     __syncthreads();
@@ -203,7 +222,7 @@ __host__ __device__ __forceinline__ size_t union_bytes(int bins) {
 // dynamic shared memory: { wh[kSortWarps][bins] (ranking)  UNION  stage[kSortSub] uint2 (permute) }
 //                        | bin_base[bins] | sub_start[bins + 1] | offs[tile_bags + 1] (FIRST)
 template <typename index_t, bool FIRST, bool LAST, bool SIDE>
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortArgs a) {
+__global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const SortArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned s_warp[kSortWarps];
     const int bins = 1 << a.bits;
@@ -242,6 +261,20 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortA
     }
     __syncthreads();
 
+    // FIRST: how the bag of a position is found.  Equal bag lengths in the tile (fixed-size bags, the
+    // benchmark and DLRM case): one multiply-high.  Otherwise: walk the boundaries from the previous item's
+    // bag (a thread's positions ascend by 32 per item).
+    bool uniform = false;
+    unsigned len0 = 0, magic = 0;
+    if (FIRST) {
+        len0 = offs[1] - offs[0];
+        bool same = true;
+        for (int j = threadIdx.x; j < nb; j += kSortThreads) same &= (offs[j + 1] - offs[j]) == len0;
+        uniform = __syncthreads_and(same) && len0 > 0 &&
+                  (unsigned long long)nb * len0 * len0 < (1ull << 32);      // q = mulhi(rel, magic) is exact
+        magic = uniform ? (unsigned)((1ull << 32) / len0) + 1u : 0u;
+    }
+
     for (long long sub = p0; sub < p1; sub += kSortSub) {
         const int n_sub = (int)min((long long)kSortSub, p1 - sub);
         for (int i = threadIdx.x; i < kSortWarps * bins; i += kSortThreads) wh[i] = 0;
@@ -254,7 +287,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortA
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
             const long long pos = wbase + k * 32;
-            key[k] = 0xffffffffu;
+            key[k] = 0;
             val[k] = 0;
             if (pos < p1) {
                 if (FIRST) {
@@ -266,46 +299,18 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortA
                 }
             }
         }
-        if (FIRST) {
-#pragma unroll
-            for (int k = 0; k < kSortItems; ++k) {
-                const long long pos = wbase + k * 32;
-                if (pos < p1) {
-                    // last bag boundary <= pos (empty bags repeat a boundary: the last one is the bag)
-                    const unsigned rel = (unsigned)(pos - p0);
-                    int j = 0;
-                    for (int step = a.tile_bags >> 1; step >= 1; step >>= 1) {
-                        const int c = j + step;
-                        if (c <= nb && offs[c] <= rel) j = c;
-                    }
-                    // c <= nb admits offs[nb] == n_tile > rel only when false, so j < nb here
-                    const long long gb = bag0 + j;
-                    const long long tt = t;
-                    const long long bb = gb - tt * a.batch;
-                    const unsigned goff4 = (unsigned)((tt * a.go_stride_t + bb * a.go_stride_b) >> 2);
-                    if (SIDE) {
-                        val[k] = (unsigned)(pos - origin);
-                        const float inv = a.mean ? 1.f / (float)(offs[j + 1] - offs[j]) : 1.f;
-                        a.goff_of[pos - origin] = goff4;
-                        a.w_of[pos - origin] = (a.psw ? a.psw[pos] : 1.f) * inv;
-                    } else {
-                        val[k] = goff4;
-                    }
-                }
-            }
-        }
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
             const bool valid = (wbase + k * 32) < p1;
-            const unsigned d = valid ? ((key[k] >> a.shift) & mask) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned d = (key[k] >> a.shift) & mask;
+            const unsigned peers = digit_peers(d, valid, a.bits);
             const int leader = __ffs(peers) - 1;
             unsigned prev = 0;
             if (valid && lane == leader) {
                 prev = my_wh[d];
                 my_wh[d] = prev + (unsigned)__popc(peers);
             }
-            prev = __shfl_sync(0xffffffffu, prev, leader);
+            prev = __shfl_sync(0xffffffffu, prev, leader & 31);
             rank[k] = prev + (unsigned)__popc(peers & lt_mask);
             __syncwarp();
         }
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortA
         __syncthreads();
         block_excl_scan(sub_start, bins, s_warp);
 
-        // ---- permute the sub-tile into digit order in shared memory (over the counters: positions first)
+        // ---- position of every lookup in the digit-ordered sub-tile (the counters die after this)
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
             if ((wbase + k * 32) < p1) {
@@ -334,7 +339,44 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const SortA
                 rank[k] += sub_start[d] + my_wh[d];
             }
         }
+        if (FIRST) {
+            // the value of a lookup: the gradient row of its bag (plain sum), or its position
+            int j = 0;
+            bool have_j = false;
+#pragma unroll
+            for (int k = 0; k < kSortItems; ++k) {
+                const long long pos = wbase + k * 32;
+                if (pos < p1) {
+                    const unsigned rel = (unsigned)(pos - p0);
+                    if (uniform) {
+                        j = len0 == 1 ? (int)rel : (int)__umulhi(rel, magic);
+                    } else if (!have_j) {
+                        // last bag boundary <= rel (empty bags repeat a boundary: the last one is the bag)
+                        j = 0;
+                        for (int step = 1 << (31 - __clz(nb)); step >= 1; step >>= 1) {
+                            const int c = j + step;
+                            if (c <= nb && offs[c] <= rel) j = c;
+                        }
+                        have_j = true;
+                    } else {
+                        while (offs[j + 1] <= rel) ++j;      // offs[nb] = lookups of the tile > rel: stops
+                    }
+                    const long long bb = (long long)tile * a.tile_bags + j;
+                    const unsigned goff4 = (unsigned)(((long long)t * a.go_stride_t + bb * a.go_stride_b) >> 2);
+                    if (SIDE) {
+                        val[k] = (unsigned)(pos - origin);
+                        const float inv = a.mean ? 1.f / (float)(offs[j + 1] - offs[j]) : 1.f;
+                        a.goff_of[pos - origin] = goff4;
+                        a.w_of[pos - origin] = (a.psw ? a.psw[pos] : 1.f) * inv;
+                    } else {
+                        val[k] = goff4;
+                    }
+                }
+            }
+        }
         __syncthreads();
+
+        // ---- permute the sub-tile into digit order in shared memory (over the counters)
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k)
             if ((wbase + k * 32) < p1) stage[rank[k]] = make_uint2(key[k], val[k]);

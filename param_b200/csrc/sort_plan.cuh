@@ -71,7 +71,7 @@ struct SortGeom {
     int passes;
     int bits[kSortMaxPasses];
     int shift[kSortMaxPasses];
-    int tile_bags;         // bags of one table per tile (a power of two)
+    int tile_bags;         // bags of one table per tile
     int tiles_per_table;
 };
 
@@ -92,9 +92,11 @@ static inline SortGeom sort_geometry(long long n_indices, int num_tables, long l
     }
     const long long bags = (long long)num_tables * batch;
     const long long avg = bags > 0 ? (n_indices + bags - 1) / bags : 1;
-    long long tb = sort_tile_target_from_env() / (avg > 0 ? avg : 1);
-    int p2 = 16;
-    while (p2 * 2 <= tb && p2 * 2 <= kSortMaxTileBags) p2 *= 2;
+    // a tile = as many bags as give ~target lookups (3 sub-tiles of 4096), a multiple of 16
+    long long tb = sort_tile_target_from_env() / (avg > 0 ? avg : 1) / 16 * 16;
+    if (tb < 16) tb = 16;
+    if (tb > kSortMaxTileBags) tb = kSortMaxTileBags;
+    const int p2 = (int)tb;
     g.tile_bags = p2;
     g.tiles_per_table = (int)((batch + p2 - 1) / p2);
     if (g.tiles_per_table < 1) g.tiles_per_table = 1;

@@ -167,3 +167,20 @@ def test_backward_with_a_plan_built_on_a_side_stream(cuda_device, exact):
     from param_b200._cabi import PB200Error
     with pytest.raises(PB200Error):
         ops.tbe_backward(planned, tro, 6, D, i_d.clone(), o_d, B, g, algo=algo, plan=plan)
+
+
+@pytest.mark.parametrize("bag", [1, 2, 20, 33])
+def test_plan_fixed_size_bags(cuda_device, bag):
+    """equal bag lengths take the multiply-high path for the bag of a position (the benchmark / DLRM case)"""
+    from param_b200 import ops
+    rows, B, D = [70_000, 9_000], 5000, 16
+    rng = np.random.default_rng(bag)
+    T = len(rows)
+    offsets = (np.arange(T * B + 1) * bag).astype(np.int64)
+    idx = np.concatenate([rng.integers(0, rows[t], size=B * bag) for t in range(T)]).astype(np.int64)
+    tro, keys, goff, order = _expected(rows, B, D, offsets, idx, "BTD")
+    plan = ops.tbe_plan(_t(tro, cuda_device), T, D, _t(idx, cuda_device), _t(offsets, cuda_device), B, 70_000)
+    torch.cuda.synchronize()
+    k, v, _, _ = _plan_arrays(plan, idx.size)
+    assert np.array_equal(k, keys)
+    assert np.array_equal(v, goff[order])
