@@ -21,11 +21,14 @@
 // grid = tiles x tables, all sizes host-known):
 //   radix_hist_kernel     digit histogram of the tile -> hist[table][tile][bin]
 //   radix_scan_kernel     per (table, bin): exclusive prefix over the tiles, bin totals
-//   radix_scatter_kernel  re-reads the tile in sub-tiles of 4096 lookups; per-warp ranking with
-//                         match.any (a warp's lanes with equal digits elect a leader that bumps the warp's
-//                         private counter: no atomics, deterministic), cross-warp and cross-bin scans in
-//                         shared memory, the sub-tile is permuted into digit order in shared memory and
-//                         written out as runs of consecutive addresses per bin.
+//   radix_scatter_kernel  re-reads the tile in sub-tiles of 4096 lookups; per-warp ranking (the lanes of a
+//                         warp that hold the same digit are found with one vote.ballot per digit bit and
+//                         elect a leader that bumps the warp's private counter: no atomics,
+//                         deterministic), cross-warp and cross-bin scans in shared memory, the sub-tile
+//                         is permuted into digit order in shared memory and written out as runs of
+//                         consecutive addresses per bin.
+// Digits are 8 or 10 bits wide (compile-time: the ballot loop is fully unrolled); all positions inside a
+// tile are 32-bit offsets from the tile's first lookup.
 // The sort is stable, so the order of equal rows — hence the summation order of the reducers — is fixed:
 // lookups of a row are summed in request order (bag-major), run to run identical.
 //
@@ -51,15 +54,15 @@ struct SortArgs {
     int mean;
     int t_base;              // first table of this launch (blockIdx.y is relative to it)
     int tile_bags, tiles_per_table;
-    int shift, bits;
+    int shift;
     const uint2 *src;        // pairs of the previous pass (nullptr: first pass, read the request)
     uint2 *dst_pairs;        // pairs for the next pass (nullptr: last pass)
     unsigned *dst_keys;      // last pass: arena rows, sorted
     unsigned *dst_vals;
     unsigned *goff_of;       // weighted / mean: per-position side arrays, written by the first pass
     float *w_of;
-    unsigned *hist;          // [T][tiles_per_table][1 << bits]
-    unsigned *bin_total;     // [T][1 << bits]
+    unsigned *hist;          // [T][tiles_per_table][1 << BITS]
+    unsigned *bin_total;     // [T][1 << BITS]
     long long *count;        // out: offsets[T * B] - offsets[0]
     int num_tables;
 };
@@ -81,72 +84,88 @@ __device__ __forceinline__ void tile_range(const SortArgs &a, int t, int tile, l
     p1 = (long long)off[tb0 + b1];
 }
 
-// Lanes of the warp that hold the same digit as this lane (only lanes with valid == true count).
-// One vote.ballot per digit bit — ~4 issue slots per bit, spread over the four schedulers of an SM.  The
-// hardware match.any did the same in one instruction but runs on the ADU pipe at ~2 cycles per lane: the
-// first version of these kernels was ADU-bound (95 % busy in the histogram, profiles/r02b_*.md).
-__device__ __forceinline__ unsigned digit_peers(unsigned d, bool valid, int bits) {
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-    for (int b = 0; b < kSortMaxDigit; ++b) {
-        if (b < bits) {                                   // warp-uniform
-            const bool bit = (d >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
-        }
+// Lanes of the warp that hold the same digit as this lane, among the lanes of `valid_mask`.
+// One vote.ballot per digit bit, fully unrolled: predicate from the bit, vote, one select, one and —
+// four issue slots per bit spread over the four schedulers of an SM.  (The hardware match.any does this in
+// one instruction but runs on the ADU pipe at ~2 cycles per lane: the first version of these kernels was
+// ADU-bound, 95 % busy in the histogram — profiles/r02b_ncu_full_sort_v1.md.)
+template <int B>
+__device__ __forceinline__ void peer_bit(unsigned &peers, unsigned d) {
+    // peers &= bit ? ballot(bit) : ~ballot(bit)   (and + setp fuse into one LOP3 with a predicate result)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, m;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "@!p not.b32 m, m;\n\t"
+        "and.b32 %0, %0, m;\n\t"
+        "}"
+        : "+r"(peers)
+        : "r"(d), "n"(1u << B));
+}
+template <int B, int BITS>
+__device__ __forceinline__ void peer_bits(unsigned &peers, unsigned d) {
+    if constexpr (B < BITS) {
+        peer_bit<B>(peers, d);
+        peer_bits<B + 1, BITS>(peers, d);
     }
+}
+template <int BITS>
+__device__ __forceinline__ unsigned digit_peers(unsigned d, unsigned valid_mask) {
+    unsigned peers = valid_mask;
+    peer_bits<0, BITS>(peers, d);
     return peers;
 }
 
 // ---- K1: digit histogram of one tile ---------------------------------------------------------------
-template <typename index_t, bool FIRST>
+template <typename index_t, bool FIRST, int BITS>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const SortArgs a) {
-    extern __shared__ unsigned s_hist[];
-    const int bins = 1 << a.bits;
-    const unsigned mask = (unsigned)bins - 1u;
+    constexpr int BINS = 1 << BITS;
+    __shared__ unsigned s_hist[BINS];
     const int t = a.t_base + blockIdx.y;
     const int tile = blockIdx.x;
     const int lane = threadIdx.x & 31;
     long long bag0, p0, p1, origin;
     int nb;
     tile_range<index_t>(a, t, tile, bag0, nb, p0, p1, origin);
-    for (int b = threadIdx.x; b < bins; b += kSortThreads) s_hist[b] = 0;
+    for (int b = threadIdx.x; b < BINS; b += kSortThreads) s_hist[b] = 0;
     if (FIRST && t == 0 && tile == 0 && threadIdx.x == 0) {
         const index_t *off = (const index_t *)a.offsets;
         *a.count = (long long)off[(long long)a.num_tables * a.batch] - origin;
     }
     __syncthreads();
-    const index_t *idx = (const index_t *)a.indices;
+    const unsigned n_tile = (unsigned)(p1 - p0);
+    const index_t *idx_t = (const index_t *)a.indices + p0;
+    const uint2 *src_t = a.src + (p0 - origin);
     constexpr int U = 4;
-    for (long long base = p0; base < p1; base += (long long)kSortThreads * U) {   // CTA-uniform trip count
+    for (unsigned base = 0; base < n_tile; base += kSortThreads * U) {   // CTA-uniform trip count
         unsigned d[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long pos = base + (long long)u * kSortThreads + threadIdx.x;
-            ok[u] = pos < p1;
-            d[u] = 0;
-            if (ok[u]) {
-                const unsigned key = FIRST ? (unsigned)ld_index<index_t>(idx + pos) : a.src[pos - origin].x;
-                d[u] = (key >> a.shift) & mask;
-            }
+            const unsigned rel = base + u * kSortThreads + threadIdx.x;
+            ok[u] = rel < n_tile;
+            unsigned key = 0;
+            if (ok[u]) key = FIRST ? (unsigned)ld_index<index_t>(idx_t + rel) : src_t[rel].x;
+            d[u] = (key >> a.shift) & (BINS - 1);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const unsigned peers = digit_peers(d[u], ok[u], a.bits);
+            const unsigned peers = digit_peers<BITS>(d[u], __ballot_sync(0xffffffffu, ok[u]));
             if (ok[u] && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d[u]], (unsigned)__popc(peers));
         }
     }
     __syncthreads();
-    unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * bins;
-    for (int b = threadIdx.x; b < bins; b += kSortThreads) h[b] = s_hist[b];
+    unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * BINS;
+    for (int b = threadIdx.x; b < BINS; b += kSortThreads) h[b] = s_hist[b];
 }
 
 // ---- K2: per (table, bin) exclusive prefix over the tiles --------------------------------------------
 // grid (ceil(bins / 32), tables); a warp = one slice of the tiles, a lane = one bin
-__global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(const SortArgs a) {
+__global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(const SortArgs a, int bins) {
     __shared__ unsigned s_sum[kSortWarps][32];
-    const int bins = 1 << a.bits;
     const int t = a.t_base + blockIdx.y;
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
@@ -177,14 +196,17 @@ __global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(const SortArgs
     }
 }
 
-// exclusive scan of n <= 256 * per values in shared memory, in place; all threads of the CTA call it
-__device__ __forceinline__ void block_excl_scan(unsigned *v, int n, unsigned *s_warp) {
+// exclusive scan of N values in shared memory, in place; all threads of the CTA call it
+template <int N>
+__device__ __forceinline__ void block_excl_scan(unsigned *v, unsigned *s_warp) {
+    constexpr int PER = (N + kSortThreads - 1) / kSortThreads;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (n + kSortThreads - 1) / kSortThreads;
-    const int lo = min(n, (int)threadIdx.x * per);
-    const int hi = min(n, lo + per);
+    const int lo = min(N, (int)threadIdx.x * PER);
+    const int hi = min(N, lo + PER);
     unsigned sum = 0;
-    for (int i = lo; i < hi; ++i) sum += v[i];
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+        if (lo + i < hi) sum += v[lo + i];
     unsigned incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -205,33 +227,36 @@ __device__ __forceinline__ void block_excl_scan(unsigned *v, int n, unsigned *s_
     }
     __syncthreads();
     unsigned run = s_warp[warp] + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned x = v[i];
-        v[i] = run;
-        run += x;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if (lo + i < hi) {
+            const unsigned x = v[lo + i];
+            v[lo + i] = run;
+            run += x;
+        }
     }
     __syncthreads();
 }
 
-__host__ __device__ __forceinline__ size_t union_bytes(int bins) {
-    const size_t a = (size_t)kSortWarps * bins * 4, b = (size_t)kSortSub * 8;
-    return a > b ? a : b;
+__host__ __device__ constexpr size_t union_bytes(int bins) {
+    return ((size_t)kSortWarps * bins * 4 > (size_t)kSortSub * 8) ? (size_t)kSortWarps * bins * 4
+                                                                   : (size_t)kSortSub * 8;
 }
 
 // ---- K3: rank and scatter one tile -------------------------------------------------------------------
-// dynamic shared memory: { wh[kSortWarps][bins] (ranking)  UNION  stage[kSortSub] uint2 (permute) }
-//                        | bin_base[bins] | sub_start[bins + 1] | offs[tile_bags + 1] (FIRST)
-template <typename index_t, bool FIRST, bool LAST, bool SIDE>
+// dynamic shared memory: { wh[kSortWarps][BINS] (ranking)  UNION  stage[kSortSub] uint2 (permute) }
+//                        | bin_base[BINS] | sub_start[BINS + 1] | offs[tile_bags + 1] (FIRST)
+template <typename index_t, bool FIRST, bool LAST, bool SIDE, int BITS>
 __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const SortArgs a) {
+    constexpr int BINS = 1 << BITS;
+    constexpr unsigned MASK = BINS - 1;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned s_warp[kSortWarps];
-    const int bins = 1 << a.bits;
-    const unsigned mask = (unsigned)bins - 1u;
     unsigned *wh = (unsigned *)s_raw;
     uint2 *stage = (uint2 *)s_raw;               // the counters are dead once the staging positions are known
-    unsigned *bin_base = (unsigned *)(s_raw + union_bytes(bins));
-    unsigned *sub_start = bin_base + bins;
-    unsigned *offs = sub_start + bins + 1;
+    unsigned *bin_base = (unsigned *)(s_raw + union_bytes(BINS));
+    unsigned *sub_start = bin_base + BINS;
+    unsigned *offs = sub_start + BINS + 1;
 
     const int t = a.t_base + blockIdx.y;
     const int tile = blockIdx.x;
@@ -241,19 +266,24 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
     int nb;
     tile_range<index_t>(a, t, tile, bag0, nb, p0, p1, origin);
     if (p1 <= p0) return;                                           // CTA-uniform
+    const unsigned n_tile = (unsigned)(p1 - p0);
     const index_t *off = (const index_t *)a.offsets;
-    const index_t *idx = (const index_t *)a.indices;
-    const long long table_p0 = (long long)off[(long long)t * a.batch] - origin;
+    const index_t *idx_t = (const index_t *)a.indices + p0;
+    const float *psw_t = a.psw ? a.psw + p0 : nullptr;
+    const unsigned rel_origin = (unsigned)(p0 - origin);            // plan position of the tile's first lookup
+    const uint2 *src_t = a.src + rel_origin;
+    const unsigned table_p0 = (unsigned)((long long)off[(long long)t * a.batch] - origin);
     const unsigned row_base = LAST ? (unsigned)a.table_row_offsets[t] : 0u;
+    const int shift = a.shift;
 
     // where this tile's lookups of every bin go: table start + bins before + same bin in earlier tiles
     {
-        const unsigned *bt = a.bin_total + (size_t)t * bins;
-        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] = bt[b];
+        const unsigned *bt = a.bin_total + (size_t)t * BINS;
+        for (int b = threadIdx.x; b < BINS; b += kSortThreads) bin_base[b] = bt[b];
         __syncthreads();
-        block_excl_scan(bin_base, bins, s_warp);
-        const unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * bins;
-        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] += (unsigned)table_p0 + h[b];
+        block_excl_scan<BINS>(bin_base, s_warp);
+        const unsigned *h = a.hist + ((size_t)t * a.tiles_per_table + tile) * BINS;
+        for (int b = threadIdx.x; b < BINS; b += kSortThreads) bin_base[b] += table_p0 + h[b];
     }
     if (FIRST) {
         // bag boundaries of the tile relative to p0; bag j of the tile covers [offs[j], offs[j + 1])
@@ -262,10 +292,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
     __syncthreads();
 
     // FIRST: how the bag of a position is found.  Equal bag lengths in the tile (fixed-size bags, the
-    // benchmark and DLRM case): one multiply-high.  Otherwise: walk the boundaries from the previous item's
-    // bag (a thread's positions ascend by 32 per item).
+    // benchmark and DLRM case): one multiply-high.  Otherwise: a binary search for the thread's first
+    // item, then a walk along the boundaries (a thread's positions ascend by 32 per item).
     bool uniform = false;
     unsigned len0 = 0, magic = 0;
+    unsigned goff_base = 0, goff_step = 0;       // gradient row of bag j of this tile, in float4 units
     if (FIRST) {
         len0 = offs[1] - offs[0];
         bool same = true;
@@ -273,27 +304,32 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
         uniform = __syncthreads_and(same) && len0 > 0 &&
                   (unsigned long long)nb * len0 * len0 < (1ull << 32);      // q = mulhi(rel, magic) is exact
         magic = uniform ? (unsigned)((1ull << 32) / len0) + 1u : 0u;
+        goff_base = (unsigned)(((long long)t * a.go_stride_t + (long long)tile * a.tile_bags * a.go_stride_b) >> 2);
+        goff_step = (unsigned)(a.go_stride_b >> 2);
     }
 
-    for (long long sub = p0; sub < p1; sub += kSortSub) {
-        const int n_sub = (int)min((long long)kSortSub, p1 - sub);
-        for (int i = threadIdx.x; i < kSortWarps * bins; i += kSortThreads) wh[i] = 0;
+    for (unsigned sub = 0; sub < n_tile; sub += kSortSub) {
+        const unsigned n_sub = min((unsigned)kSortSub, n_tile - sub);
+        {
+            uint4 *z = (uint4 *)wh;
+            for (int i = threadIdx.x; i < kSortWarps * BINS / 4; i += kSortThreads) z[i] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
 
         // ---- load + per-warp ranking: warp w owns lookups [w * 32 * ITEMS, +32 * ITEMS) of the sub-tile
         unsigned key[kSortItems], val[kSortItems], rank[kSortItems];
-        unsigned *my_wh = wh + warp * bins;
-        const long long wbase = sub + (long long)warp * 32 * kSortItems + lane;
+        unsigned *my_wh = wh + warp * BINS;
+        const unsigned wbase = sub + warp * 32 * kSortItems + lane;   // item k: position wbase + 32 k of the tile
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
-            const long long pos = wbase + k * 32;
+            const unsigned rel = wbase + k * 32;
             key[k] = 0;
             val[k] = 0;
-            if (pos < p1) {
+            if (rel < n_tile) {
                 if (FIRST) {
-                    key[k] = (unsigned)ld_index<index_t>(idx + pos);
+                    key[k] = (unsigned)ld_index<index_t>(idx_t + rel);
                 } else {
-                    const uint2 pr = a.src[pos - origin];
+                    const uint2 pr = src_t[rel];
                     key[k] = pr.x;
                     val[k] = pr.y;
                 }
@@ -301,43 +337,41 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
         }
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
-            const bool valid = (wbase + k * 32) < p1;
-            const unsigned d = (key[k] >> a.shift) & mask;
-            const unsigned peers = digit_peers(d, valid, a.bits);
-            const int leader = __ffs(peers) - 1;
+            const bool valid = (wbase + k * 32) < n_tile;
+            const unsigned d = (key[k] >> shift) & MASK;
+            const unsigned peers = digit_peers<BITS>(d, __ballot_sync(0xffffffffu, valid));
+            const int leader = (__ffs(peers) - 1) & 31;
             unsigned prev = 0;
             if (valid && lane == leader) {
                 prev = my_wh[d];
                 my_wh[d] = prev + (unsigned)__popc(peers);
             }
-            prev = __shfl_sync(0xffffffffu, prev, leader & 31);
+            prev = __shfl_sync(0xffffffffu, prev, leader);
             rank[k] = prev + (unsigned)__popc(peers & lt_mask);
             __syncwarp();
         }
         __syncthreads();
 
         // ---- per bin: exclusive prefix over the warps (in place), count of the CTA -> sub_start
-        for (int b = threadIdx.x; b < bins; b += kSortThreads) {
+        for (int b = threadIdx.x; b < BINS; b += kSortThreads) {
             unsigned run = 0;
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
-                const unsigned v = wh[w * bins + b];
-                wh[w * bins + b] = run;
+                const unsigned v = wh[w * BINS + b];
+                wh[w * BINS + b] = run;
                 run += v;
             }
             sub_start[b] = run;
         }
-        if (threadIdx.x == 0) sub_start[bins] = (unsigned)n_sub;
+        if (threadIdx.x == 0) sub_start[BINS] = n_sub;
         __syncthreads();
-        block_excl_scan(sub_start, bins, s_warp);
+        block_excl_scan<BINS>(sub_start, s_warp);
 
         // ---- position of every lookup in the digit-ordered sub-tile (the counters die after this)
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
-            if ((wbase + k * 32) < p1) {
-                const unsigned d = (key[k] >> a.shift) & mask;
-                rank[k] += sub_start[d] + my_wh[d];
-            }
+            const unsigned d = (key[k] >> shift) & MASK;
+            rank[k] += sub_start[d] + my_wh[d];      // lookups past the tile end read bin 0: harmless
         }
         if (FIRST) {
             // the value of a lookup: the gradient row of its bag (plain sum), or its position
@@ -345,9 +379,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
             bool have_j = false;
 #pragma unroll
             for (int k = 0; k < kSortItems; ++k) {
-                const long long pos = wbase + k * 32;
-                if (pos < p1) {
-                    const unsigned rel = (unsigned)(pos - p0);
+                const unsigned rel = wbase + k * 32;
+                if (rel < n_tile) {
                     if (uniform) {
                         j = len0 == 1 ? (int)rel : (int)__umulhi(rel, magic);
                     } else if (!have_j) {
@@ -361,13 +394,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
                     } else {
                         while (offs[j + 1] <= rel) ++j;      // offs[nb] = lookups of the tile > rel: stops
                     }
-                    const long long bb = (long long)tile * a.tile_bags + j;
-                    const unsigned goff4 = (unsigned)(((long long)t * a.go_stride_t + bb * a.go_stride_b) >> 2);
+                    const unsigned goff4 = goff_base + (unsigned)j * goff_step;
                     if (SIDE) {
-                        val[k] = (unsigned)(pos - origin);
+                        val[k] = rel_origin + rel;
                         const float inv = a.mean ? 1.f / (float)(offs[j + 1] - offs[j]) : 1.f;
-                        a.goff_of[pos - origin] = goff4;
-                        a.w_of[pos - origin] = (a.psw ? a.psw[pos] : 1.f) * inv;
+                        a.goff_of[rel_origin + rel] = goff4;
+                        a.w_of[rel_origin + rel] = (psw_t ? psw_t[rel] : 1.f) * inv;
                     } else {
                         val[k] = goff4;
                     }
@@ -379,23 +411,27 @@ __global__ void __launch_bounds__(kSortThreads, 2) radix_scatter_kernel(const So
         // ---- permute the sub-tile into digit order in shared memory (over the counters)
 #pragma unroll
         for (int k = 0; k < kSortItems; ++k)
-            if ((wbase + k * 32) < p1) stage[rank[k]] = make_uint2(key[k], val[k]);
+            if ((wbase + k * 32) < n_tile) stage[rank[k]] = make_uint2(key[k], val[k]);
         __syncthreads();
 
         // ---- write out: consecutive threads -> consecutive addresses inside a bin's run
-        for (int i = threadIdx.x; i < n_sub; i += kSortThreads) {
-            const uint2 pr = stage[i];
-            const unsigned d = (pr.x >> a.shift) & mask;
-            const unsigned o = bin_base[d] + ((unsigned)i - sub_start[d]);
-            if (LAST) {
-                a.dst_keys[o] = pr.x + row_base;
-                a.dst_vals[o] = pr.y;
-            } else {
-                a.dst_pairs[o] = pr;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            const unsigned i = threadIdx.x + k * kSortThreads;
+            if (i < n_sub) {
+                const uint2 pr = stage[i];
+                const unsigned d = (pr.x >> shift) & MASK;
+                const unsigned o = bin_base[d] + (i - sub_start[d]);
+                if (LAST) {
+                    a.dst_keys[o] = pr.x + row_base;
+                    a.dst_vals[o] = pr.y;
+                } else {
+                    a.dst_pairs[o] = pr;
+                }
             }
         }
         __syncthreads();
-        for (int b = threadIdx.x; b < bins; b += kSortThreads) bin_base[b] += sub_start[b + 1] - sub_start[b];
+        for (int b = threadIdx.x; b < BINS; b += kSortThreads) bin_base[b] += sub_start[b + 1] - sub_start[b];
         // the barrier after the next sub-tile's counter reset orders this update before its readers
     }
 }
@@ -414,28 +450,35 @@ static int set_smem(Kern k, size_t bytes) {
     return PB200_OK;
 }
 
-template <typename index_t, bool FIRST, bool LAST>
+template <typename index_t, bool FIRST, bool LAST, int BITS>
 static int launch_pass(const SortArgs &a, bool side, dim3 grid, cudaStream_t st) {
-    const size_t hist_smem = ((size_t)1 << a.bits) * 4;
-    radix_hist_kernel<index_t, FIRST><<<grid, kSortThreads, hist_smem, st>>>(a);
+    radix_hist_kernel<index_t, FIRST, BITS><<<grid, kSortThreads, 0, st>>>(a);
     PB200_LAUNCH_CHECK();
-    dim3 sgrid((unsigned)(((1u << a.bits) + 31) / 32), grid.y);
-    radix_scan_kernel<<<sgrid, kSortThreads, 0, st>>>(a);
+    dim3 sgrid((unsigned)(((1u << BITS) + 31) / 32), grid.y);
+    radix_scan_kernel<<<sgrid, kSortThreads, 0, st>>>(a, 1 << BITS);
     PB200_LAUNCH_CHECK();
-    const size_t smem = scatter_smem_bytes(a.bits, a.tile_bags, FIRST);
+    const size_t smem = scatter_smem_bytes(BITS, a.tile_bags, FIRST);
     int rc;
     if (FIRST && side) {
-        auto k = radix_scatter_kernel<index_t, FIRST, LAST, true>;
+        auto k = radix_scatter_kernel<index_t, FIRST, LAST, true, BITS>;
         if ((rc = set_smem(k, smem)) != PB200_OK) return rc;
         k<<<grid, kSortThreads, smem, st>>>(a);
     } else {
-        auto k = radix_scatter_kernel<index_t, FIRST, LAST, false>;
+        auto k = radix_scatter_kernel<index_t, FIRST, LAST, false, BITS>;
         if ((rc = set_smem(k, smem)) != PB200_OK) return rc;
         k<<<grid, kSortThreads, smem, st>>>(a);
     }
     PB200_LAUNCH_CHECK();
     count_launch(3);
     return PB200_OK;
+}
+
+template <typename index_t, int BITS>
+static int launch_pass_fl(const SortArgs &a, bool side, bool first, bool last, dim3 grid, cudaStream_t st) {
+    if (first && last) return launch_pass<index_t, true, true, BITS>(a, side, grid, st);
+    if (first) return launch_pass<index_t, true, false, BITS>(a, side, grid, st);
+    if (last) return launch_pass<index_t, false, true, BITS>(a, side, grid, st);
+    return launch_pass<index_t, false, false, BITS>(a, side, grid, st);
 }
 
 template <typename index_t>
@@ -445,7 +488,6 @@ static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void 
     const SortGeom g = sort_geometry(p.n_indices, p.num_tables, p.batch, max_table_rows);
     unsigned char *base = (unsigned char *)plan;
     // tables per launch: all of them by default; PB200_SORT_GROUP = g runs the passes group by group
-    // (the group's pairs then stay closer to L2 between the kernels of a pass)
     static const int group_env = [] {
         const char *e = getenv("PB200_SORT_GROUP");
         return e ? atoi(e) : 0;
@@ -485,7 +527,6 @@ static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void 
         for (int ps = 0; ps < g.passes; ++ps) {
             const bool first = ps == 0, last = ps == g.passes - 1;
             a.shift = g.shift[ps];
-            a.bits = g.bits[ps];
             // pass ps writes buffer (passes - 1 - ps) & 1: 0 = out area, 1 = tmp
             uint2 *wr = ((g.passes - 1 - ps) & 1) ? tmp : out_as_pairs;
             const uint2 *rd = ((g.passes - ps) & 1) ? tmp : out_as_pairs;
@@ -494,10 +535,9 @@ static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void 
             a.dst_keys = last ? keys : nullptr;
             a.dst_vals = last ? vals : nullptr;
             int rc;
-            if (first && last) rc = launch_pass<index_t, true, true>(a, side, grid, st);
-            else if (first) rc = launch_pass<index_t, true, false>(a, side, grid, st);
-            else if (last) rc = launch_pass<index_t, false, true>(a, side, grid, st);
-            else rc = launch_pass<index_t, false, false>(a, side, grid, st);
+            if (g.bits[ps] == 8) rc = launch_pass_fl<index_t, 8>(a, side, first, last, grid, st);
+            else if (g.bits[ps] == 10) rc = launch_pass_fl<index_t, 10>(a, side, first, last, grid, st);
+            else rc = PB200_EUNSUPPORTED;
             if (rc != PB200_OK) return rc;
         }
     }

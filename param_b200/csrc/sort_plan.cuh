@@ -45,18 +45,9 @@ static inline int bits_for(unsigned long long n) {
     return b;
 }
 
-constexpr int kSortMaxPasses = 8;
-constexpr int kSortMaxDigit = 11;      // 8 warp histograms of 2^11 counters + staging still fit one CTA
+constexpr int kSortMaxPasses = 4;
+constexpr int kSortMaxDigit = 10;      // digits are 8 or 10 bits wide (compile-time variants of the kernels)
 constexpr int kSortMaxTileBags = 2048;
-
-static inline int sort_digit_from_env() {
-    static const int v = [] {
-        const char *e = getenv("PB200_SORT_DIGIT");   // widest radix digit (bits) of one pass
-        const int x = e ? atoi(e) : 10;
-        return (x >= 4 && x <= kSortMaxDigit) ? x : 10;
-    }();
-    return v;
-}
 
 static inline long long sort_tile_target_from_env() {
     static const long long v = [] {
@@ -80,15 +71,20 @@ static inline SortGeom sort_geometry(long long n_indices, int num_tables, long l
                                      long long max_table_rows) {
     SortGeom g{};
     const int key_bits = max_table_rows > 0 ? bits_for((unsigned long long)max_table_rows) : 32;
-    const int maxd = sort_digit_from_env();
-    g.passes = (key_bits + maxd - 1) / maxd;
-    int left = key_bits, sh = 0;
-    for (int p = 0; p < g.passes; ++p) {
-        const int b = (left + (g.passes - p) - 1) / (g.passes - p);
-        g.bits[p] = b;
-        g.shift[p] = sh;
-        sh += b;
-        left -= b;
+    // fewest passes of 8- or 10-bit digits that cover the key: 1-8 bits -> 8; 9-10 -> 10; 11-16 -> 8+8;
+    // 17-20 -> 10+10 (a 1 M-row table); 21-24 -> 8+8+8 (10 M rows); 25-30 -> 10+10+10; 31-32 -> 4 x 8
+    int passes = 1, width = 8;
+    if (key_bits <= 8) passes = 1, width = 8;
+    else if (key_bits <= 10) passes = 1, width = 10;
+    else if (key_bits <= 16) passes = 2, width = 8;
+    else if (key_bits <= 20) passes = 2, width = 10;
+    else if (key_bits <= 24) passes = 3, width = 8;
+    else if (key_bits <= 30) passes = 3, width = 10;
+    else passes = 4, width = 8;
+    g.passes = passes;
+    for (int p = 0; p < passes; ++p) {
+        g.bits[p] = width;
+        g.shift[p] = p * width;
     }
     const long long bags = (long long)num_tables * batch;
     const long long avg = bags > 0 ? (n_indices + bags - 1) / bags : 1;
@@ -115,7 +111,7 @@ static inline PlanLayout plan_layout(long long n_indices, int num_tables, long l
     PlanLayout L{};
     const SortGeom g = sort_geometry(n_indices, num_tables, batch, 0);
     const size_t arr = ((size_t)n_indices * 4 + 255) & ~(size_t)255;
-    const size_t bins = (size_t)1 << sort_digit_from_env();
+    const size_t bins = (size_t)1 << kSortMaxDigit;
     L.keys = 0;
     L.vals = arr;
     L.goff_of = 2 * arr;
