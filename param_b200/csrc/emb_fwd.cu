@@ -24,6 +24,8 @@
 
 namespace pb200 {
 
+int launch_fwd_hot(const FwdParams &p, int idx_type, cudaStream_t st);   // emb_fwd_hot.cu
+
 // ------------------------------------------------------------------------------------
 // DIRECT variant
 // ------------------------------------------------------------------------------------
@@ -448,8 +450,24 @@ static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t
         PB200_LAUNCH_CHECK();
         return PB200_OK;
     }
-    // measured on B200 (profiles/): DIRECT beats STAGED by 15-35 %, so AUTO = DIRECT
-    if (algo == PB200_FWD_AUTO) algo = PB200_FWD_DIRECT;
+    // measured on B200 (profiles/): DIRECT beats STAGED by 15-35 %; HOT (emb_fwd_hot.cu: persistent CTAs with
+    // the head of every table cached in shared memory) beats DIRECT under skew.  AUTO = HOT where it
+    // applies (TBE layout, fp32, 64 < dim <= 256, enough bags to fill the persistent grid), else DIRECT.
+    {
+        const int idx_type = sizeof(index_t) == 8 ? PB200_IDX_I64 : PB200_IDX_I32;
+        static const int auto_hot = [] {
+            const char *e = getenv("PB200_FWD_AUTO_HOT");
+            return e ? atoi(e) : 1;
+        }();
+        const bool hot_ok = p.table_row_offsets && !p.weights_f16 && p.has_last_offset && (p.dim >> 2) > 16 &&
+                            (p.dim >> 2) <= 64;
+        if (algo == PB200_FWD_AUTO)
+            algo = (hot_ok && auto_hot && p.n_bags >= 32768) ? PB200_FWD_HOT : PB200_FWD_DIRECT;
+        if (algo == PB200_FWD_HOT) {
+            if (hot_ok) return launch_fwd_hot(p, idx_type, st);
+            algo = PB200_FWD_DIRECT;
+        }
+    }
     // bulk copies need 16 B-aligned index/offset arrays
     if ((((uintptr_t)p.indices | (uintptr_t)p.offsets) & 15) != 0) algo = PB200_FWD_DIRECT;
     if (algo == PB200_FWD_STAGED) {
@@ -488,7 +506,7 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_HOT) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weights;
     p.table_row_offsets = (const long long *)table_row_offsets;
@@ -556,7 +574,7 @@ extern "C" int pb200_embbag_fwd(const float *weight, int64_t num_rows, int32_t d
     if (num_rows < 0 || dim < 1 || n_bags < 0 || n_indices < 0 || out_row_stride < dim)
         return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_HOT) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weight;
     p.table_row_offsets = nullptr;

@@ -1,9 +1,9 @@
 """Drop the B200 kernels under the UNMODIFIED reference runners.
 
-Needs the reference importable as `param_bench` (the reference's own import convention,
-train/comms/pt/comms.py:15-36; e.g. `ln -s <param checkout> /tmp/pb/param_bench` and
-PYTHONPATH=/tmp/pb:<param checkout>/train/comms/pt).  On a box without the reference use the
-stand-alone runners in param_b200/comms/pt/ instead.
+The reference tree is found by param_b200/integration/refpath.py ($PARAM_REF, baseline/_ref — an unedited copy
+made by tools/make_baseline_ref.sh that travels to the GPU box —, /root/reference) and exposed as
+`param_bench`, the reference's own import convention (train/comms/pt/comms.py:15-36).  On a box without the
+reference use the stand-alone runners in param_b200/comms/pt/ instead.
 
     # config 3 — the reference's comms.py, b200 backend selected through its own plugin registry
     torchrun --nproc-per-node 8 -- -m param_b200.integration.param_plugin comms \
@@ -16,6 +16,12 @@ stand-alone runners in param_b200/comms/pt/ instead.
 
     # config 1 — the reference's compute driver with the module swapped (nn.EmbeddingBag -> B200)
     python -m param_b200.integration.param_plugin emb --device gpu emb --dataset A
+
+    # config 5 — the reference's replay tools on a trace captured with tools/cfg5_capture.py
+    torchrun --nproc-per-node 8 -m param_b200.integration.param_plugin comm_replay --trace-type et \
+        --trace-path <dir> --backend b200
+    torchrun --nproc-per-node 8 -m param_b200.integration.param_plugin et_replay --trace-path <dir> -m full \
+        --replay-config param_b200/et/replay-config-b200-aten.json --backend b200
 """
 from __future__ import annotations
 
@@ -112,10 +118,43 @@ def run_emb(argv):
     driver.main()
 
 
+def _register_et_backend_if_cuda(argv):
+    """--backend b200 needs the class in et_replay's registry BEFORE its parser computes the choices
+    (et_replay/comm/comms_utils.py:1446-1451)."""
+    if "b200" in argv:
+        from ..et.backend import register_et_backend
+        register_et_backend("b200")
+
+
+def run_comm_replay(argv):
+    """the reference's et_replay/tools/comm_replay.py, unmodified; `--backend b200` routes every replayed
+    all_to_all(v) to the peer-push kernel (comm_replay.py:1734-1761 picks customized_backend[...])"""
+    _register_et_backend_if_cuda(argv)
+    from et_replay.tools import comm_replay
+
+    sys.argv = ["comm_replay.py"] + list(argv)
+    comm_replay.main()
+
+
+def run_et_replay(argv):
+    """the reference's et_replay/tools/et_replay.py, unmodified: compute nodes are rebuilt from name +
+    schema (the replay config's "import modules" pulls in param_b200.et / the aten override), comm nodes go to
+    the backend chosen with --backend"""
+    _register_et_backend_if_cuda(argv)
+    from et_replay.tools import et_replay
+
+    sys.argv = ["et_replay.py"] + list(argv)
+    et_replay.main()
+
+
 def main():
-    if len(sys.argv) < 2 or sys.argv[1] not in ("comms", "dlrm", "emb"):
-        raise SystemExit("usage: param_plugin {comms|dlrm|emb} <runner args>")
-    {"comms": run_comms, "dlrm": run_dlrm, "emb": run_emb}[sys.argv[1]](sys.argv[2:])
+    runners = {"comms": run_comms, "dlrm": run_dlrm, "emb": run_emb, "comm_replay": run_comm_replay,
+               "et_replay": run_et_replay}
+    if len(sys.argv) < 2 or sys.argv[1] not in runners:
+        raise SystemExit("usage: param_plugin {comms|dlrm|emb|comm_replay|et_replay} <runner args>")
+    from . import refpath
+    refpath.setup()
+    runners[sys.argv[1]](sys.argv[2:])
 
 
 if __name__ == "__main__":

@@ -57,6 +57,8 @@ for exact in (False, True):
     res[f"inline_{tag}"] = ev(lambda: ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out,
                                                        scale=-1e-6, algo=tag, max_table_rows=rows))
 res["fwd"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out))
+res["fwd_direct"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out, algo="direct"))
+res["fwd_hot"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out, algo="hot"))
 buf = ops.tbe_plan(arena.row_offsets, T, D, idx, off, B, rows).buf
 
 
