@@ -6,21 +6,22 @@ made by tools/make_baseline_ref.sh that travels to the GPU box —, /root/refere
 reference use the stand-alone runners in param_b200/comms/pt/ instead.
 
     # config 3 — the reference's comms.py, b200 backend selected through its own plugin registry
-    torchrun --nproc-per-node 8 -- -m param_b200.integration.param_plugin comms \
+    torchrun --nproc-per-node 8 -m -- param_b200.integration.param_plugin comms \
         --backend b200 --device cuda --collective all_to_all_single --b 1K --e 1G --z 1 --c 1
+    #   (`-m --`: torchrun's own parser otherwise claims the runner's short options --e / --n / --b)
     #   (comms.py falls through to customized_backend[args.backend], comms.py:1506-1521)
 
     # config 4 — the reference's dlrm.py (backend class is hard-coded there, dlrm.py:1327-1333, so it
     # is patched in; the use_device_time shim fixes the reference's start-up crash)
-    torchrun --nproc-per-node 8 -- -m param_b200.integration.param_plugin dlrm --mini-batch-size 8192 ...
+    torchrun --nproc-per-node 8 -m -- param_b200.integration.param_plugin dlrm --mini-batch-size 8192 ...
 
     # config 1 — the reference's compute driver with the module swapped (nn.EmbeddingBag -> B200)
     python -m param_b200.integration.param_plugin emb --device gpu emb --dataset A
 
     # config 5 — the reference's replay tools on a trace captured with tools/cfg5_capture.py
-    torchrun --nproc-per-node 8 -m param_b200.integration.param_plugin comm_replay --trace-type et \
+    torchrun --nproc-per-node 8 -m -- param_b200.integration.param_plugin comm_replay --trace-type et \
         --trace-path <dir> --backend b200
-    torchrun --nproc-per-node 8 -m param_b200.integration.param_plugin et_replay --trace-path <dir> -m full \
+    torchrun --nproc-per-node 8 -m -- param_b200.integration.param_plugin et_replay --trace-path <dir> -m full \
         --replay-config param_b200/et/replay-config-b200-aten.json --backend b200
 """
 from __future__ import annotations
@@ -90,7 +91,11 @@ def run_dlrm(argv):
         return args
 
     dlrm.commsDLRMBench.readArgs = read_args
-    dlrm.PyTorchDistBackend = cls
+    # PB200_PLUGIN_BACKEND=stock keeps the reference's own PyTorchDistBackend (c10d / NCCL): the comparator
+    # run of the very same script
+    import os
+    if os.environ.get("PB200_PLUGIN_BACKEND", "b200") != "stock":
+        dlrm.PyTorchDistBackend = cls
     sys.argv = ["dlrm.py"] + list(argv)
     dlrm.main()
 

@@ -38,6 +38,7 @@ def find_reference() -> Optional[Path]:
 
 
 def _stub_missing_third_party() -> None:
+    import torch  # noqa: F401  (torch.fx probes `import pydot` itself: it must see the truth, before the stand-in exists)
     for name in ("pydot", "intervaltree"):
         if name in sys.modules:
             continue
@@ -46,6 +47,8 @@ def _stub_missing_third_party() -> None:
         except ImportError:
             mod = types.ModuleType(name)
             mod.__doc__ = "empty stand-in registered by param_b200.integration.refpath (module absent from the image)"
+            if name == "pydot":
+                mod.Dot = type("Dot", (), {})
             if name == "intervaltree":
                 mod.Interval = type("Interval", (), {})
                 mod.IntervalTree = type("IntervalTree", (), {})

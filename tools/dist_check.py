@@ -88,6 +88,32 @@ with torch.cuda.stream(st):
 st.synchronize()
 report("all_to_all_single inside a replayed CUDA graph", torch.equal(zc, ref))
 
+# staged output next to LIVE window tensors (the staging area used to be window offset 0, where the
+# bump allocator puts ipTensor): the input lives in the window, the output does not, three iterations
+win.reset_alloc()
+xin_w, _ = win.alloc(n * world, torch.float32)
+xin_w.copy_(x)
+got = torch.empty_like(ref)
+ok = True
+for _ in range(3):
+    got.zero_()
+    win.all_to_all_single(got, xin_w)
+    ok &= torch.equal(got, ref) and torch.equal(xin_w, x)
+report("all_to_all_single staged output beside a live in-window input (3 iterations)", ok)
+# list form: dist.all_to_all(list, list) as ONE push kernel, ragged blocks, outputs outside / inside the window
+sizes = rng.integers(0, 3000, size=(world, world))
+ins_l = [torch.arange(int(sizes[rank][d]), device=dev, dtype=torch.float32) + 1000 * rank + d for d in range(world)]
+ref_l = [torch.empty(int(sizes[s][rank]), device=dev) for s in range(world)]
+dist.all_to_all(ref_l, ins_l)
+got_l = [torch.empty_like(t) for t in ref_l]
+win.all_to_all(got_l, ins_l)
+report("all_to_all (list form) staged outputs == c10d", all(torch.equal(a, b_) for a, b_ in zip(got_l, ref_l)))
+got_w = [win.alloc(int(sizes[s][rank]), torch.float32)[0] for s in range(world)]
+for _ in range(2):
+    win.all_to_all(got_w, ins_l)
+report("all_to_all (list form) outputs in the window, written in place == c10d",
+       all(torch.equal(a, b_) for a, b_ in zip(got_w, ref_l)) and torch.equal(xin_w, x))
+
 # ---- 3. fused pooled exchange vs the reference's cat + a2a + cat --------------------------------
 T_g, b, E = 3 * world + 1, 64, 128
 ts, bs = split_lengths(T_g, world), [b] * world
