@@ -10,9 +10,9 @@
 // it with the streaming cold rows, the hit rate is 50 %, and every miss is a 512 B round trip to L2 —
 // 86 GB of L2 -> SM traffic per step at cfg2, which is what bounds that kernel (ncu: no unit saturated, DRAM at
 // 31 %, profiles/r01c_ncu_full_fwd_256tables.md).  Here:
-//   * persistent grid, ONE CTA of 32 warps per SM, each CTA owns a contiguous range of bags (table-major), so
-//     it changes table two or three times in its life;
-//   * on a table change the CTA copies the head of the table (K rows, 128 KB at dim 128) into shared memory
+//   * persistent grid, ONE CTA of 32 warps per SM; all CTAs walk the tables in the same order, each taking
+//     every gridDim-th group of 32 bags of the current table (all SMs stay on one table: L2 locality as DIRECT);
+//   * at every table the CTA copies the head of the table (K rows, 128 KB at dim 128) into shared memory
 //     with cp.async.bulk (TMA unit, SASS UBLKCP) on an mbarrier — one copy per SM instead of one L1 image
 //     per resident CTA;
 //   * a lookup whose row is < K is served by LDS.128, the others by the same LDG.128 path as DIRECT.  With
@@ -25,7 +25,7 @@
 
 namespace pb200 {
 
-constexpr int kHotThreads = 1024;
+constexpr int kHotThreads = 768;
 constexpr int kHotWarps = kHotThreads / 32;
 constexpr unsigned kHotCopyChunk = 32768;   // bytes per bulk copy
 
@@ -38,9 +38,25 @@ struct HotAccum {
         for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
+    // one 16 B vector of a row: from the shared-memory image if the row is cached (warp-uniform predicate), else
+    // from global memory — two predicated loads into the same registers, no select, no branch
+    static __device__ __forceinline__ float4 ld_row(unsigned hot, unsigned saddr, const float4 *gptr) {
+        float4 v;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.u32 p, %4, 0;\n\t"
+            "@p ld.shared.v4.f32 {%0,%1,%2,%3}, [%5];\n\t"
+            "@!p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%6];\n\t"
+            "}"
+            : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+            : "r"(hot), "r"(saddr), "l"(gptr));
+        return v;
+    }
+
     // N rows whose table-relative ids sit in lanes j .. j+N-1 of my_rel
     template <int N>
-    __device__ __forceinline__ void batch(const float4 *const (&gcol)[C], const float4 *const (&scol)[C],
+    __device__ __forceinline__ void batch(const float4 *const (&gcol)[C], const unsigned (&scol)[C],
                                           unsigned vec4, unsigned hot_n, unsigned my_rel, float my_w, int j) {
         float4 v[N][C];
         float wv[N];
@@ -48,14 +64,11 @@ struct HotAccum {
         for (int u = 0; u < N; ++u) {
             const unsigned rel = __shfl_sync(0xffffffffu, my_rel, j + u);
             if (WEIGHTED) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u);
-            const unsigned roff = rel * vec4;          // used for cached rows only (rel < hot_n)
-            if (rel < hot_n) {                          // warp-uniform
+            const unsigned hot = rel < hot_n ? 1u : 0u;                  // warp-uniform
+            const unsigned soff = (hot ? rel : 0u) * vec4 * 16u;         // cached rows only
 #pragma unroll
-                for (int c = 0; c < C; ++c) v[u][c] = scol[c][roff];
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(gcol[c] + (unsigned long long)rel * vec4);
-            }
+            for (int c = 0; c < C; ++c)
+                v[u][c] = ld_row(hot, scol[c] + soff, gcol[c] + (unsigned long long)rel * vec4);
         }
 #pragma unroll
         for (int u = 0; u < N; ++u) {
@@ -74,8 +87,7 @@ struct HotAccum {
 };
 
 template <typename index_t, int C, bool WEIGHTED>
-__global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdParams p, int hot_cap,
-                                                                     long long bags_per_cta) {
+__global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdParams p, int hot_cap) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     // rows in flight per lane: 4 (x 32 warps per SM = 64 KB of requests in flight, several times the
@@ -83,9 +95,6 @@ __global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdPa
     constexpr int U = (C == 1) ? 4 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned vec4 = (unsigned)(p.dim >> 2);
-    const long long gb0 = (long long)blockIdx.x * bags_per_cta;
-    const long long gb1 = min(p.n_bags, gb0 + bags_per_cta);
-    if (gb0 >= gb1) return;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         mbar_fence_init();
@@ -94,11 +103,14 @@ __global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdPa
     unsigned phase = 0;
     const index_t *off = (const index_t *)p.offsets;
     const index_t *idx = (const index_t *)p.indices;
-    const float4 *s_hot = (const float4 *)s_raw;
-
-    for (long long t = gb0 / p.batch; t * p.batch < gb1; ++t) {
-        const long long lo = max(gb0, t * p.batch);
-        const long long hi = min(gb1, (t + 1) * p.batch);
+    const unsigned s_base = smem_u32(s_raw);
+    // Every CTA walks the tables in the same order and takes every gridDim-th group of 32 bags of the current
+    // table: at any moment all SMs gather from the same table, so its warm rows (beyond the cached head) are
+    // shared through L2 exactly as under DIRECT's linear block order.  (The first version gave each CTA one
+    // contiguous range of bags: 148 CTAs in 148 different places of the arena, L2 hit rate 12 % instead of
+    // 55 %, 2.6x the DRAM reads — profiles/r02f_ncu_fwd_hot_v1.md.)
+    const unsigned stride = gridDim.x * kHotWarps;
+    for (int t = 0; t < p.num_tables; ++t) {
         const long long base_row = p.table_row_offsets[t];
         const long long rows_t = p.table_row_offsets[t + 1] - base_row;
         const unsigned hot_n = (unsigned)min((long long)hot_cap, rows_t);
@@ -116,17 +128,17 @@ __global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdPa
         }
         const float4 *gtab = (const float4 *)p.weights + (unsigned long long)base_row * vec4;
         const float4 *gcol[C];
-        const float4 *scol[C];
+        unsigned scol[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const unsigned col = (unsigned)(c * 32 + lane);
             gcol[c] = gtab + (col < vec4 ? col : 0);
-            scol[c] = s_hot + (col < vec4 ? col : 0);
+            scol[c] = s_base + (col < vec4 ? col : 0) * 16u;
         }
-        const index_t *off_t = off + lo;
-        const unsigned n_here = (unsigned)(hi - lo);
-        float *out_t = p.out + t * p.out_stride_t + (lo - t * p.batch) * p.out_stride_b;
-        for (unsigned r = warp; r < n_here; r += kHotWarps) {
+        const index_t *off_t = off + (long long)t * p.batch;
+        const unsigned n_here = (unsigned)p.batch;
+        float *out_t = p.out + t * p.out_stride_t;
+        for (unsigned r = blockIdx.x * kHotWarps + warp; r < n_here; r += stride) {
             const long long begin = ld_index<index_t>(off_t + r);
             const int len = (int)(ld_index<index_t>(off_t + r + 1) - begin);
             const index_t *ip = idx + begin + lane;
@@ -142,10 +154,6 @@ __global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdPa
                 const int cnt = min(32, len - base);
                 int j = 0;
                 for (; j + U <= cnt; j += U) a.template batch<U>(gcol, scol, vec4, hot_n, my_rel, my_w, j);
-                if (U > 4 && j + 4 <= cnt) {
-                    a.template batch<4>(gcol, scol, vec4, hot_n, my_rel, my_w, j);
-                    j += 4;
-                }
                 if (U > 2 && j + 2 <= cnt) {
                     a.template batch<2>(gcol, scol, vec4, hot_n, my_rel, my_w, j);
                     j += 2;
@@ -159,12 +167,12 @@ __global__ void __launch_bounds__(kHotThreads, 1) tbe_fwd_hot_kernel(const FwdPa
             for (int c = 0; c < C; ++c) {
                 const unsigned col = (unsigned)(c * 32 + lane);
                 if (col < vec4) {
-                    float4 r = a.acc[c];
+                    float4 rr = a.acc[c];
                     if (p.mean) {
-                        r.x = __fdiv_rn(r.x, cntf); r.y = __fdiv_rn(r.y, cntf);
-                        r.z = __fdiv_rn(r.z, cntf); r.w = __fdiv_rn(r.w, cntf);
+                        rr.x = __fdiv_rn(rr.x, cntf); rr.y = __fdiv_rn(rr.y, cntf);
+                        rr.z = __fdiv_rn(rr.z, cntf); rr.w = __fdiv_rn(rr.w, cntf);
                     }
-                    st_stream_f4(o + col, r);
+                    st_stream_f4(o + col, rr);
                 }
             }
         }
@@ -191,11 +199,10 @@ static int launch_hot(const FwdParams &p, cudaStream_t st) {
     if (smem > 48 * 1024)
         PB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = sm_count();                                     // persistent: one CTA per SM
-    const long long min_bags = 4 * kHotWarps;
-    if (grid * min_bags > p.n_bags) grid = (p.n_bags + min_bags - 1) / min_bags;
+    const long long groups = (p.batch + kHotWarps - 1) / kHotWarps;  // groups of 32 bags per table
+    if (grid > groups) grid = groups;
     if (grid < 1) grid = 1;
-    const long long per = (p.n_bags + grid - 1) / grid;
-    kern<<<(unsigned)grid, kHotThreads, smem, st>>>(p, (int)k, per);
+    kern<<<(unsigned)grid, kHotThreads, smem, st>>>(p, (int)k);
     count_launch();
     PB200_LAUNCH_CHECK();
     return PB200_OK;

@@ -291,9 +291,58 @@ def gen_tbe_optim():
     print("wrote tbe_optim_torch.npz")
 
 
+def gen_tbe_rowwise():
+    """fbgemm's exact rowwise Adagrad on NON-constant gradients, computed with torch only and independently of
+    oracle/: the dense gradient of every table comes from torch autograd (nn.EmbeddingBag, sparse=False, a random
+    incoming gradient, one step with per-sample weights), the update is written out in float64 exactly as
+    published — m[row] += mean_d(g[row, d]^2);  w[row] -= lr / (sqrt(m[row]) + eps) * g[row] — for the rows the
+    batch touched.  Three steps, state carried over."""
+    torch.manual_seed(11)
+    rng = np.random.default_rng(20261018)
+    rows, dim, B, lr, eps, steps = [90, 17, 400], 24, 48, 0.07, 1.0e-8, 3
+    T = len(rows)
+    w = [(torch.randn(r, dim) * 0.1).double() for r in rows]
+    m = [torch.zeros(r, dtype=torch.float64) for r in rows]
+    out = {"rows": np.array(rows), "dim": dim, "batch": B, "lr": lr, "eps": eps, "steps": steps,
+           "w0": torch.cat(w).float().numpy()}
+    for s in range(steps):
+        lens = rng.integers(0, 11, size=T * B)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        idx = np.concatenate([rng.integers(0, rows[t], size=int(lens[t * B:(t + 1) * B].sum()))
+                              for t in range(T)]).astype(np.int64)
+        psw = (rng.random(idx.size).astype(np.float32) + 0.5) if s == 1 else None
+        grad = torch.from_numpy(rng.standard_normal((B, T * dim)).astype(np.float32))
+        out[f"s{s}_indices"], out[f"s{s}_offsets"], out[f"s{s}_grad"] = idx, offsets, grad.numpy()
+        out[f"s{s}_psw"] = psw if psw is not None else np.zeros(0, np.float32)
+        pooled, embs = [], []
+        for t in range(T):
+            e = nn.EmbeddingBag(rows[t], dim, mode="sum", _weight=w[t].float().clone())
+            lo, hi = offsets[t * B], offsets[(t + 1) * B]
+            pw = None if psw is None else torch.from_numpy(psw[lo:hi])
+            pooled.append(e(torch.from_numpy(idx[lo:hi]), torch.from_numpy(offsets[t * B:(t + 1) * B] - lo),
+                            per_sample_weights=pw))
+            embs.append(e)
+        fwd_out = torch.cat(pooled, dim=1)
+        fwd_out.backward(grad)
+        for t, e in enumerate(embs):
+            g = e.weight.grad.double()                                   # dense dW of the table, from autograd
+            touched = torch.zeros(rows[t], dtype=torch.bool)
+            lo, hi = offsets[t * B], offsets[(t + 1) * B]
+            touched[torch.from_numpy(idx[lo:hi])] = True
+            m[t] = torch.where(touched, m[t] + (g * g).mean(dim=1), m[t])
+            step = lr / (m[t].sqrt() + eps)
+            w[t] = torch.where(touched[:, None], w[t] - step[:, None] * g, w[t])
+        out[f"s{s}_out"] = fwd_out.detach().numpy().copy()
+        out[f"s{s}_w"] = torch.cat(w).numpy().copy()                    # float64
+        out[f"s{s}_state"] = torch.cat(m).numpy().copy()
+    np.savez_compressed(HERE / "tbe_rowwise_adagrad_torch.npz", **out)
+    print("wrote tbe_rowwise_adagrad_torch.npz")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tbe_optim":      # torch only: no reference import needed
         gen_tbe_optim()
+        gen_tbe_rowwise()
         raise SystemExit(0)
     if not REF.exists():
         raise SystemExit("/root/reference not present: golden vectors can only be regenerated "
@@ -303,3 +352,4 @@ if __name__ == "__main__":
     gen_dlrm_sparse()
     gen_a2a()
     gen_tbe_optim()
+    gen_tbe_rowwise()

@@ -347,3 +347,22 @@ def test_tbe_training_steps_match_torch_optim_golden(cuda_device, golden_dir):
                 assert _rel(op.weights.cpu().numpy(), d[f"{name}_s{s}_w"]) <= RTOL, (name, bwd_algo, s)
             if name == "adagrad":
                 assert _rel(op.momentum1.cpu().numpy(), d["adagrad_state"]) <= RTOL
+
+
+def test_rowwise_adagrad_matches_torch_only_golden_on_nonconstant_gradients(cuda_device, golden_dir):
+    """tests/golden/tbe_rowwise_adagrad_torch.npz — exact rowwise Adagrad with random incoming gradients and one
+    weighted step, computed with torch only (autograd dense gradients + the published update in float64).
+    B200TBE (pb200_tbe_bwd_fused) must follow it step for step, weights and state: 1e-5 relative."""
+    from param_b200.compute.tbe import B200TBE
+    d = np.load(golden_dir / "tbe_rowwise_adagrad_torch.npz")
+    rows, dim = [int(r) for r in d["rows"]], int(d["dim"])
+    op = B200TBE([(r, dim) for r in rows], optimizer="exact_row_wise_adagrad", learning_rate=float(d["lr"]),
+                 eps=float(d["eps"]), device=cuda_device)
+    op.weights.copy_(_t(d["w0"], cuda_device))
+    for s in range(int(d["steps"])):
+        psw = _t(d[f"s{s}_psw"], cuda_device) if d[f"s{s}_psw"].size else None
+        out = op.forward(_t(d[f"s{s}_indices"], cuda_device), _t(d[f"s{s}_offsets"], cuda_device), psw)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), d[f"s{s}_out"], rtol=RTOL, atol=1e-6)
+        out.backward(_t(d[f"s{s}_grad"], cuda_device))
+        assert _rel(op.weights.cpu().numpy(), d[f"s{s}_w"]) <= RTOL, s
+        assert _rel(op.momentum1.cpu().numpy(), d[f"s{s}_state"]) <= RTOL, s

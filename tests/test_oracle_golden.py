@@ -172,3 +172,24 @@ def test_oracle_training_steps_match_torch_optim_golden(oracle, golden_dir):
             np.testing.assert_allclose(w, d[f"{name}_s{s}_w"], rtol=1e-5, atol=1e-6, err_msg=f"{name} step {s}")
         if m is not None:
             np.testing.assert_allclose(m, d["adagrad_state"], rtol=1e-5, atol=1e-7)
+
+
+def test_oracle_rowwise_adagrad_matches_torch_only_golden_on_nonconstant_gradients(oracle, golden_dir):
+    """tests/golden/tbe_rowwise_adagrad_torch.npz: exact rowwise Adagrad with RANDOM incoming gradients (so
+    mean_d(g^2) is a real mean, not a constant), one weighted step; dense gradients from torch autograd, the
+    update written out in float64 by the committed script — independent of this oracle.  Pins the restated
+    fbgemm formula on general gradients (round 1 pinned it on row-constant gradients only)."""
+    d = np.load(golden_dir / "tbe_rowwise_adagrad_torch.npz")
+    rows, dim, B = d["rows"], int(d["dim"]), int(d["batch"])
+    lr, eps = float(d["lr"]), float(d["eps"])
+    tro = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    w, m = d["w0"].astype(np.float64), None
+    for s in range(int(d["steps"])):
+        idx, off, grad = d[f"s{s}_indices"], d[f"s{s}_offsets"], d[f"s{s}_grad"]
+        psw = d[f"s{s}_psw"] if d[f"s{s}_psw"].size else None
+        out = oracle.tbe_fwd(w.astype(np.float32), tro, dim, idx, off, B, psw=psw)
+        np.testing.assert_allclose(out, d[f"s{s}_out"], rtol=1e-5, atol=1e-6)
+        g = oracle.tbe_bwd(int(tro[-1]), tro, dim, idx, off, B, grad, psw=psw, dtype=np.float64)
+        w, m = oracle.fused_optimizer_step(w, g, "exact_row_wise_adagrad", lr=lr, eps=eps, state=m)
+        np.testing.assert_allclose(w, d[f"s{s}_w"], rtol=1e-5, atol=1e-7, err_msg=f"step {s}")
+        np.testing.assert_allclose(m, d[f"s{s}_state"], rtol=1e-5, atol=1e-9, err_msg=f"state, step {s}")
