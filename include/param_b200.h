@@ -50,10 +50,6 @@ extern "C" {
 #define PB200_FWD_DIRECT 1 /* one lane-group per bag, indices read straight from HBM  */
 #define PB200_FWD_STAGED 2 /* persistent CTAs, cp.async.bulk (TMA) index staging      */
 #define PB200_FWD_PIPELINED 3 /* persistent CTAs, register software pipeline over bags  */
-#define PB200_FWD_HOT 4    /* persistent CTAs, one per SM; the first rows of every table (the popular
-                            * ones under the reference's Zipf generator, pytorch_emb.py:138-160) are
-                            * copied into shared memory with cp.async.bulk (TMA) and served from
-                            * there; TBE layout, fp32, 64 < dim <= 256 (AUTO picks it there)   */
 
 /* backward kernel variants */
 #define PB200_BWD_AUTO 0

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
 
 POOL_SUM, POOL_MEAN = 0, 1
 IDX_I64, IDX_I32 = 0, 1
-FWD_AUTO, FWD_DIRECT, FWD_STAGED, FWD_PIPELINED, FWD_HOT = 0, 1, 2, 3, 4
+FWD_AUTO, FWD_DIRECT, FWD_STAGED, FWD_PIPELINED = 0, 1, 2, 3
 BWD_AUTO, BWD_ATOMIC, BWD_SORTED, BWD_EXACT = 0, 1, 2, 3
 W_F32, W_F16 = 0, 1
 OPT_SGD, OPT_ROWWISE_ADAGRAD = 1, 2

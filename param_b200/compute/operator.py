@@ -45,6 +45,7 @@ class B200BatchedEmbeddingBagOp:
         if mode is None:
             raise PB200Error("pooling must be 0 (sum) or 1 (mean)")
         self.weighted = bool(weighted)
+        self.op = None                                       # release the previous build's tables first
         # the reference's wrapper hard-codes stochastic_rounding=True (:292); it only acts on fp16 tables
         self.op = B200TBE(list(zip(rows_list, dims_list)), learning_rate=lr, eps=eps, pooling_mode=mode,
                           optimizer=str(getattr(optimizer, "value", optimizer)),
@@ -52,7 +53,10 @@ class B200BatchedEmbeddingBagOp:
                           stochastic_rounding=True, device=torch.device(dev))
 
     def cleanup(self) -> None:
-        self.op = self.fwd_out = self.grad_in = None
+        # the framework calls this before every build AND after every input run (build_executor.py:158, :229):
+        # only the outputs go, so that several inputs can run against one build (the reference wrapper drops
+        # the op too, :303-307, and then fails on the second input of a build)
+        self.fwd_out = self.grad_in = None
 
     def forward(self, *args, **kwargs):
         indices, offsets = args[0], args[1]

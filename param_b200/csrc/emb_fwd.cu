@@ -24,12 +24,10 @@
 
 namespace pb200 {
 
-int launch_fwd_hot(const FwdParams &p, int idx_type, cudaStream_t st);   // emb_fwd_hot.cu
-
 // ------------------------------------------------------------------------------------
 // DIRECT variant
 // ------------------------------------------------------------------------------------
-template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float>
+template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float, bool HEAD = false>
 __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     constexpr int BPW = 32 / G;  // bags per warp
     constexpr int U = UnrollFor<C>::value;
@@ -53,8 +51,9 @@ __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
     const long long base_row = (active && p.table_row_offsets) ? p.table_row_offsets[t] : 0;
 
-    BagAccum<index_t, G, C, WEIGHTED, U, WT> acc;
+    BagAccum<index_t, G, C, WEIGHTED, U, WT, HEAD> acc;
     acc.zero();
+    if (HEAD) acc.head_end = (unsigned)base_row + (unsigned)p.head_rows;
     acc.template run<false>(p, (const index_t *)p.indices + begin,
                             WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen, maxlen,
                             lane_g, vec4);
@@ -64,6 +63,11 @@ __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
 template <typename index_t, int G, int C, bool WEIGHTED>
 __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) {
     tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
+}
+// head rows of every table keep L1 priority, cold rows bypass L1 (PB200_FWD_HEAD_ROWS, fp32, unweighted)
+template <typename index_t, int G, int C>
+__global__ void __launch_bounds__(256, 4) tbe_fwd_direct_head_kernel(const FwdParams p) {
+    tbe_fwd_direct_body<index_t, G, C, false, float, true>(p);
 }
 // same body compiled for 5 resident CTAs/SM (48 registers): selectable with PB200_FWD_OCC5=1
 template <typename index_t, int G, int C, bool WEIGHTED>
@@ -419,6 +423,8 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
             tbe_fwd_direct_f16_kernel<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (weighted)
             tbe_fwd_direct_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
+        else if (p.head_rows > 0 && p.table_row_offsets)
+            tbe_fwd_direct_head_kernel<index_t, G, C><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (occ5)
             tbe_fwd_direct_kernel_occ5<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
         else
@@ -450,24 +456,12 @@ static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t
         PB200_LAUNCH_CHECK();
         return PB200_OK;
     }
-    // measured on B200 (profiles/): DIRECT beats STAGED by 15-35 %; HOT (emb_fwd_hot.cu: persistent CTAs with
-    // the head of every table cached in shared memory) beats DIRECT under skew.  AUTO = HOT where it
-    // applies (TBE layout, fp32, 64 < dim <= 256, enough bags to fill the persistent grid), else DIRECT.
-    {
-        const int idx_type = sizeof(index_t) == 8 ? PB200_IDX_I64 : PB200_IDX_I32;
-        static const int auto_hot = [] {
-            const char *e = getenv("PB200_FWD_AUTO_HOT");
-            return e ? atoi(e) : 1;
-        }();
-        const bool hot_ok = p.table_row_offsets && !p.weights_f16 && p.has_last_offset && (p.dim >> 2) > 16 &&
-                            (p.dim >> 2) <= 64;
-        if (algo == PB200_FWD_AUTO)
-            algo = (hot_ok && auto_hot && p.n_bags >= 32768) ? PB200_FWD_HOT : PB200_FWD_DIRECT;
-        if (algo == PB200_FWD_HOT) {
-            if (hot_ok) return launch_fwd_hot(p, idx_type, st);
-            algo = PB200_FWD_DIRECT;
-        }
-    }
+    // measured on B200 (profiles/): DIRECT beats STAGED by 15-35 %, so AUTO = DIRECT.  (A persistent variant with
+    // the head of every table staged into shared memory by cp.async.bulk was built and measured in round 2:
+    // 4.30 ms with one contiguous bag range per CTA, 6.26 ms with all CTAs walking the tables in lockstep,
+    // against 3.09 ms for DIRECT at 64 tables under Zipf 1.15 — profiles/r02f_ncu_fwd_hot_v1.md,
+    // r02h_*.log; removed.)
+    if (algo == PB200_FWD_AUTO) algo = PB200_FWD_DIRECT;
     // bulk copies need 16 B-aligned index/offset arrays
     if ((((uintptr_t)p.indices | (uintptr_t)p.offsets) & 15) != 0) algo = PB200_FWD_DIRECT;
     if (algo == PB200_FWD_STAGED) {
@@ -506,7 +500,7 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
         return PB200_EINVAL;
     if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_HOT) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weights;
     p.table_row_offsets = (const long long *)table_row_offsets;
@@ -523,6 +517,13 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
     p.dim = dim;
     p.has_last_offset = 1;
     p.mean = pool_mode == PB200_POOL_MEAN;
+    {
+        static const int head_rows = [] {
+            const char *e = getenv("PB200_FWD_HEAD_ROWS");
+            return e ? atoi(e) : 0;
+        }();
+        p.head_rows = head_rows;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     // Contract (param_b200.h): the arena holds fewer than 2^32 rows — arena row ids are 32-bit inside
     // the kernels.  table_row_offsets lives on the device, so the bound is the caller's to keep
@@ -574,7 +575,7 @@ extern "C" int pb200_embbag_fwd(const float *weight, int64_t num_rows, int32_t d
     if (num_rows < 0 || dim < 1 || n_bags < 0 || n_indices < 0 || out_row_stride < dim)
         return PB200_EINVAL;
     if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
-    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_HOT) return PB200_EINVAL;
+    if (algo < PB200_FWD_AUTO || algo > PB200_FWD_PIPELINED) return PB200_EINVAL;
     FwdParams p{};
     p.weights = weight;
     p.table_row_offsets = nullptr;

@@ -18,6 +18,10 @@ reference use the stand-alone runners in param_b200/comms/pt/ instead.
     # config 1 — the reference's compute driver with the module swapped (nn.EmbeddingBag -> B200)
     python -m param_b200.integration.param_plugin emb --device gpu emb --dataset A
 
+    # compute/python framework — the reference's run_benchmark.py with the B200 operator + its JSON config
+    python -m param_b200.integration.param_plugin bench -c param_b200/compute/configs/b200_batched_embedding_bag.json \
+        -d cuda -w 2 -i 5 -b --cuda-l2-cache on
+
     # config 5 — the reference's replay tools on a trace captured with tools/cfg5_capture.py
     torchrun --nproc-per-node 8 -m -- param_b200.integration.param_plugin comm_replay --trace-type et \
         --trace-path <dir> --backend b200
@@ -152,11 +156,19 @@ def run_et_replay(argv):
     et_replay.main()
 
 
+def run_bench(argv):
+    """the reference's train/compute/python/pytorch/run_benchmark.py with the B200 operator, input iterator and
+    input-data generator registered (param_b200/compute/python_plugin.py) and _clear_cache taught sm_100"""
+    from ..compute import python_plugin
+
+    python_plugin.run_benchmark(argv)
+
+
 def main():
     runners = {"comms": run_comms, "dlrm": run_dlrm, "emb": run_emb, "comm_replay": run_comm_replay,
-               "et_replay": run_et_replay}
+               "et_replay": run_et_replay, "bench": run_bench}
     if len(sys.argv) < 2 or sys.argv[1] not in runners:
-        raise SystemExit("usage: param_plugin {comms|dlrm|emb|comm_replay|et_replay} <runner args>")
+        raise SystemExit("usage: param_plugin {comms|dlrm|emb|comm_replay|et_replay|bench} <runner args>")
     from . import refpath
     refpath.setup()
     runners[sys.argv[1]](sys.argv[2:])

@@ -18,8 +18,7 @@ from ._cabi import (BWD_ATOMIC, BWD_AUTO, BWD_EXACT, BWD_SORTED, FWD_AUTO, FWD_D
                     W_F16, W_F32, PB200Error)
 
 _MODE = {"sum": POOL_SUM, "mean": POOL_MEAN}
-_FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED, "pipelined": _cabi.FWD_PIPELINED,
-             "hot": _cabi.FWD_HOT}
+_FWD_ALGO = {"auto": FWD_AUTO, "direct": FWD_DIRECT, "staged": FWD_STAGED, "pipelined": _cabi.FWD_PIPELINED}
 _BWD_ALGO = {"auto": BWD_AUTO, "atomic": BWD_ATOMIC, "sorted": BWD_SORTED, "exact": BWD_EXACT}
 # fbgemm OptimType values as they appear in the reference's op configs
 # (split_table_batched_embeddings_ops.py:290 `OptimType(optimizer)`)

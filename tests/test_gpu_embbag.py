@@ -77,7 +77,7 @@ def _random_tbe(rng, T, B, dim, max_len, rows_lo=50, rows_hi=400, fixed_len=None
 
 
 @pytest.mark.parametrize("dim", [128, 64, 56, 256, 8])
-@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined", "hot"])
+@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined"])
 @pytest.mark.parametrize("layout", ["BTD", "TBD"])
 def test_tbe_forward_vs_oracle_ragged(cuda_device, oracle, dim, algo, layout):
     from param_b200 import ops
@@ -90,7 +90,7 @@ def test_tbe_forward_vs_oracle_ragged(cuda_device, oracle, dim, algo, layout):
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined", "hot"])
+@pytest.mark.parametrize("algo", ["direct", "staged", "pipelined"])
 def test_tbe_forward_odd_alignment_and_tail(cuda_device, oracle, algo):
     """odd total index count, odd bag starts, int32 indices: exercises the 16 B alignment logic of
     the bulk-copy staging and its direct fallback on the last tile."""
@@ -112,7 +112,7 @@ def test_tbe_forward_mean_and_weighted(cuda_device, oracle):
     rows, tro, arena, offsets, idx = _random_tbe(rng, T, B, dim, 30)
     psw = rng.random(idx.size).astype(np.float32) + 0.5
     ar = ops.TableArena(_t(arena, cuda_device), _t(tro, cuda_device), list(rows), dim)
-    for algo in ("direct", "staged", "pipelined", "hot"):
+    for algo in ("direct", "staged", "pipelined"):
         out = ops.tbe_forward(ar, _t(idx, cuda_device), _t(offsets, cuda_device), B, mode="mean", algo=algo)
         np.testing.assert_allclose(out.cpu().numpy(), oracle.tbe_fwd(arena, tro, dim, idx, offsets, B, mode="mean"),
                                    rtol=RTOL, atol=1e-6)
@@ -227,8 +227,7 @@ def test_large_shape_properties(cuda_device):
     out_d = ops.tbe_forward(ar, idx, off, B, algo="direct")
     out_s = ops.tbe_forward(ar, idx, off, B, algo="staged")
     out_p = ops.tbe_forward(ar, idx, off, B, algo="pipelined")
-    out_h = ops.tbe_forward(ar, idx, off, B, algo="hot")
-    assert torch.equal(out_d, out_s) and torch.equal(out_d, out_p) and torch.equal(out_d, out_h)   # bit for bit
+    assert torch.equal(out_d, out_s) and torch.equal(out_d, out_p)       # variants agree bit for bit
     # linearity: lookup(2W) == 2 lookup(W) exactly (power-of-two scaling commutes with rounding)
     ar.weights.mul_(2.0)
     assert torch.equal(ops.tbe_forward(ar, idx, off, B), out_d * 2.0)
@@ -383,34 +382,3 @@ def test_operator_plugin_runs(cuda_device, oracle):
     assert np.abs(op.op.weights.detach().cpu().numpy() - want).max() <= RTOL * np.abs(want).max()
     op.cleanup()
     assert op.op is None
-
-
-@pytest.mark.parametrize("dim", [128, 256, 96])
-@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
-def test_tbe_forward_hot_row_cache(cuda_device, oracle, dim, idx_dtype):
-    """the HOT variant (csrc/emb_fwd_hot.cu): persistent CTAs whose chunks of bags straddle table boundaries
-    (several cache refills per CTA), tables smaller and larger than the cache, rows on both sides of the
-    cache boundary, ragged and empty bags, weighted — bit-exact against the oracle for SUM"""
-    from param_b200 import ops
-    rng = np.random.default_rng(dim)
-    rows = [40, 5000, 300, 100_000, 256, 257, 1]
-    T, B = len(rows), 1500
-    tro = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
-    arena = rng.standard_normal((int(tro[-1]), dim)).astype(np.float32)
-    lens = rng.integers(0, 40, size=T * B)
-    lens[rng.random(T * B) < 0.1] = 0
-    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    idx = np.empty(int(offsets[-1]), np.int64)
-    for t in range(T):
-        lo, hi = offsets[t * B], offsets[(t + 1) * B]
-        hot = rng.random(hi - lo) < 0.6            # most lookups near the head of the table, some anywhere
-        idx[lo:hi] = np.where(hot, rng.integers(0, min(rows[t], 300), size=hi - lo), rng.integers(0, rows[t], size=hi - lo))
-    ar = ops.TableArena(_t(arena, cuda_device), _t(tro, cuda_device), rows, dim)
-    i_d, o_d = _t(idx, cuda_device, idx_dtype), _t(offsets, cuda_device, idx_dtype)
-    out = ops.tbe_forward(ar, i_d, o_d, B, algo="hot")
-    assert np.array_equal(out.cpu().numpy(), oracle.tbe_fwd(arena, tro, dim, idx, offsets, B))
-    assert torch.equal(out, ops.tbe_forward(ar, i_d, o_d, B, algo="direct"))
-    psw = rng.random(idx.size).astype(np.float32)
-    outw = ops.tbe_forward(ar, i_d, o_d, B, per_sample_weights=_t(psw, cuda_device), algo="hot", layout="TBD")
-    assert torch.equal(outw, ops.tbe_forward(ar, i_d, o_d, B, per_sample_weights=_t(psw, cuda_device),
-                                             algo="direct", layout="TBD"))

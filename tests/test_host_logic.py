@@ -400,3 +400,36 @@ def test_comms_compute_runner_flags_match_the_reference_names():
     assert a.mode == "compute" and a.num_emb_tables_per_device == 4 and a.num_compute == 7 and a.b == "2M"
     with pytest.raises(SystemExit):
         _args(["--kernel", "gemm"])            # dense kernels are outside the hot path
+
+
+def test_compute_python_plugin_registers_iterator_generator_and_clear_cache():
+    """f2: operator + input iterator + input-data generator in the reference's registries, same JSON schema as
+    the reference's split_table_batched_embeddings_ops.json; _clear_cache gets the sm_100 entry."""
+    import json
+    from param_b200.integration import refpath
+    if refpath.setup(require=False) is None:
+        pytest.skip("reference tree not present")
+    from param_b200.compute import python_plugin as pp
+    pp.register_all()
+    pp.register_all()                                   # idempotent
+    from param_bench.train.compute.python.lib import data as d, iterator as it, operator as o
+    from param_bench.train.compute.python.lib.pytorch import op_executor
+    assert pp.OP_NAME in o.op_map and pp.ITERATOR_NAME in it.config_iterator_map
+    assert pp.GENERATOR_NAME in d.data_generator_map and op_executor._clear_cache._pb200
+    cfg = json.loads((ROOT / "param_b200" / "compute" / "configs" / "b200_batched_embedding_bag.json").read_text())
+    spec = cfg[pp.OP_NAME]
+    assert spec["input_iterator"] == pp.ITERATOR_NAME and spec["input_data_generator"] == pp.GENERATOR_NAME
+    c0 = spec["config"][0]
+    build = {"args": c0["build"][0]["args"], "kwargs": c0["build"][0]["kwargs"]}
+    runs = list(it.config_iterator_map[pp.ITERATOR_NAME]({"build": build, "input": c0["input"]}, "input", "cpu"))
+    assert [a["value"] for a in runs[0][1]["args"]] == [16, 1000000, 128, 65536, 20, False, "fp32"]
+    ic = runs[0][1]
+    ic["args"][0]["value"], ic["args"][1]["value"], ic["args"][3]["value"], ic["args"][4]["value"] = 3, 50, 6, 4
+    (idx, off, w), kw = d.data_generator_map[pp.GENERATOR_NAME]().get_data(ic, "cpu", alpha=1.0)
+    assert idx.numel() == 3 * 6 * 4 and off.tolist() == list(range(0, 73, 4)) and w is None and kw == {}
+    assert int(idx.max()) < 50 and int(idx.min()) >= 0
+    # the reference's alpha convention: 0 -> arange % L, <= 0.5 -> arange % E, > 1 -> Zipf % E
+    i0, o0, _ = pp.generate_requests(4, 3, 10, 0, alpha=0.0)
+    assert i0.tolist() == [0, 1, 2] * 4 and o0.tolist() == [0, 3, 6, 9, 12]
+    i1, o1, w1 = pp.generate_requests(4, 3, 10, 12, alpha=1.2, weighted=True)
+    assert o1.tolist() == [15, 18, 21, 24] and int(i1.max()) < 10 and w1.numel() == 12

@@ -47,6 +47,11 @@ def ev(fn, n=5):
 
 
 res = {}
+if os.environ.get("PB200_SORT_BENCH_FWD_ONLY"):
+    f = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out, algo="direct"), n=10)
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("PB200_")}
+    print(f"T={T} alpha={alpha} rows={rows} knobs={knobs} fwd_direct {f:.3f} ms")
+    sys.exit(0)
 for exact in (False, True):
     tag = "exact" if exact else "sorted"
     buf = ops.tbe_plan(arena.row_offsets, T, D, idx, off, B, rows, exact=exact).buf
@@ -58,7 +63,6 @@ for exact in (False, True):
                                                        scale=-1e-6, algo=tag, max_table_rows=rows))
 res["fwd"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out))
 res["fwd_direct"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out, algo="direct"))
-res["fwd_hot"] = ev(lambda: ops.tbe_forward(arena, idx, off, B, out=out, algo="hot"))
 buf = ops.tbe_plan(arena.row_offsets, T, D, idx, off, B, rows).buf
 
 
