@@ -188,6 +188,18 @@ int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32_t num_tabl
                   float scale, int32_t algo, int64_t max_table_rows,
                   void *scratch, int64_t scratch_bytes, int32_t plan_ready, void *stream);
 
+/* Sparse form of the single-table backward: the VALUES of the uncoalesced COO gradient that
+ * nn.EmbeddingBag(sparse=True) hands to autograd (the reference allocates its tables that way,
+ * train/comms/pt/pytorch_dist_backend.py:923-934; ATen: _embedding_bag_sparse_backward).
+ *   values[i, :] = psw[i] * grad_out[bag(i), :]   (MEAN: divided by the bag length), i < n_indices
+ * The COO indices are the lookup indices themselves, so the gradient of a table costs
+ * n_indices * dim * 4 bytes instead of a dense zero-filled [num_rows, dim] buffer.
+ * grad_out: fp32, row b at grad_out + b*go_row_stride; offsets as in pb200_embbag_fwd. */
+int pb200_embbag_bwd_sparse(const float *grad_out, int64_t go_row_stride, int32_t dim,
+                            const void *offsets, int64_t n_bags, int32_t include_last_offset,
+                            int64_t n_indices, int32_t idx_type, const float *psw, int32_t pool_mode,
+                            float *values /* [n_indices, dim] */, void *stream);
+
 /* =========================================================================
  * 3b. Backward with the optimizer fused in ("exact": one update per touched row)
  * =========================================================================

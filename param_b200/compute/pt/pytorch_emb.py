@@ -30,21 +30,29 @@ from ..._cabi import PB200Error
 # ---------------------------------------------------------------------------------------------
 class _EmbeddingBagFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weight, indices, offsets, psw, mode, include_last_offset, fwd_algo, bwd_algo):
+    def forward(ctx, weight, indices, offsets, psw, mode, include_last_offset, fwd_algo, bwd_algo, sparse):
         out = ops.embedding_bag_forward(weight, indices, offsets, mode=mode,
                                         per_sample_weights=psw,
                                         include_last_offset=include_last_offset, algo=fwd_algo)
         ctx.save_for_backward(indices, offsets, psw if psw is not None else torch.empty(0))
-        ctx.meta = (tuple(weight.shape), mode, include_last_offset, psw is not None, bwd_algo)
+        ctx.meta = (tuple(weight.shape), mode, include_last_offset, psw is not None, bwd_algo, sparse)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         indices, offsets, psw = ctx.saved_tensors
-        (rows, dim), mode, include_last, weighted, bwd_algo = ctx.meta
+        (rows, dim), mode, include_last, weighted, bwd_algo, sparse = ctx.meta
         dev = grad_out.device
         indices = indices.contiguous().view(-1)
         offsets = offsets.contiguous().view(-1)
+        if sparse:
+            # nn.EmbeddingBag(sparse=True): an uncoalesced COO gradient with one entry per lookup — what the
+            # reference's tables produce (pytorch_dist_backend.py:923-934) — instead of a dense zero-filled
+            # [rows, dim] buffer (5.1 GB for a 10 M x 128 table)
+            g = ops.embedding_bag_backward_sparse(grad_out.contiguous(), indices, offsets, rows, mode=mode,
+                                                  per_sample_weights=psw if weighted else None,
+                                                  include_last_offset=include_last)
+            return g, None, None, None, None, None, None, None, None
         if not include_last:  # the batched kernel wants B+1 offsets
             offsets = torch.cat([offsets, torch.tensor([indices.numel()], dtype=offsets.dtype, device=dev)])
         n_bags = offsets.numel() - 1
@@ -53,7 +61,7 @@ class _EmbeddingBagFn(torch.autograd.Function):
         ops.tbe_backward(grad_w, row_off, 1, dim, indices, offsets, n_bags, grad_out.contiguous(),
                          layout="TBD", scale=1.0, mode=mode,
                          per_sample_weights=psw if weighted else None, algo=bwd_algo)
-        return grad_w, None, None, None, None, None, None, None
+        return grad_w, None, None, None, None, None, None, None, None
 
 
 class B200EmbeddingBag(nn.Module):
@@ -90,7 +98,7 @@ class B200EmbeddingBag(nn.Module):
                 raise PB200Error("offsets required for 1-D indices")
             ilo = self.include_last_offset
         return _EmbeddingBagFn.apply(self.weight, indices, offsets, per_sample_weights, self.mode,
-                                     ilo, self.fwd_algo, self.bwd_algo)
+                                     ilo, self.fwd_algo, self.bwd_algo, self.sparse)
 
     def extra_repr(self) -> str:
         return f"{self.num_embeddings}, {self.embedding_dim}, mode={self.mode!r}"

@@ -121,6 +121,49 @@ __global__ void __launch_bounds__(256) tbe_bwd_generic_kernel(const BwdParams p)
 }
 
 // ------------------------------------------------------------------------------------
+// SPARSE: the values of the uncoalesced COO gradient nn.EmbeddingBag(sparse=True) produces
+// ------------------------------------------------------------------------------------
+// values[i, :] = w_i * grad_out[bag(i), :] for every lookup i (ATen: _embedding_bag_sparse_backward ->
+// index_select of grad by offset2bag, scaled; the reference allocates its tables with sparse=True,
+// pytorch_dist_backend.py:923-934).  One warp per bag: the gradient row is read once and written once per
+// lookup of the bag, 16 B per lane, so a table's gradient costs nnz * dim * 4 bytes instead of a dense
+// rows * dim * 4 zero-filled buffer (5.1 GB for a 10 M x 128 table).
+template <typename index_t>
+__global__ void __launch_bounds__(256) embbag_bwd_sparse_values_kernel(
+    const float *__restrict__ grad_out, long long go_row_stride, int dim, const index_t *__restrict__ offsets,
+    long long n_bags, int has_last, long long n_indices, const float *__restrict__ psw, int mean,
+    float *__restrict__ values) {
+    const int lane = threadIdx.x & 31;
+    const long long bag = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bag >= n_bags) return;
+    const long long begin = (long long)offsets[bag];
+    const long long end = (bag + 1 < n_bags || has_last) ? (long long)offsets[bag + 1] : n_indices;
+    const float inv = (mean && end > begin) ? 1.f / (float)(end - begin) : 1.f;
+    const float *g = grad_out + bag * go_row_stride;
+    const bool vec = (dim % 4 == 0) && ((((uintptr_t)g | (uintptr_t)values) & 15) == 0);
+    if (vec) {
+        const int v4 = dim >> 2;
+        for (int c = lane; c < v4; c += 32) {
+            float4 x = ld_stream_f4((const float4 *)g + c);
+            x.x *= inv; x.y *= inv; x.z *= inv; x.w *= inv;
+            for (long long i = begin; i < end; ++i) {
+                float4 y = x;
+                if (psw) {
+                    const float w = psw[i];
+                    y.x *= w; y.y *= w; y.z *= w; y.w *= w;
+                }
+                st_stream_f4((float4 *)(values + i * dim) + c, y);
+            }
+        }
+    } else {
+        for (int d = lane; d < dim; d += 32) {
+            const float x = g[d] * inv;
+            for (long long i = begin; i < end; ++i) values[i * dim + d] = psw ? x * psw[i] : x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // SORTED (pair builder, scratch plan and chunk pipeline: emb_bwd_common.cuh)
 // ------------------------------------------------------------------------------------
 // step 3: segmented reduce over the sorted pairs.  One lane group per kSeg sorted entries.
@@ -450,4 +493,31 @@ extern "C" int pb200_tbe_bwd(float *dst, const int64_t *table_row_offsets, int32
     if (idx_type == PB200_IDX_I32)
         return dispatch_bwd<int>(p, algo, idx_type, max_table_rows, scratch, scratch_bytes, ready, st);
     return PB200_EINVAL;
+}
+
+extern "C" int pb200_embbag_bwd_sparse(const float *grad_out, int64_t go_row_stride, int32_t dim,
+                                       const void *offsets, int64_t n_bags, int32_t include_last_offset,
+                                       int64_t n_indices, int32_t idx_type, const float *psw,
+                                       int32_t pool_mode, float *values, void *stream) {
+    if (!grad_out || !values || (!offsets && n_bags > 0)) return PB200_EINVAL;
+    if (dim < 1 || n_bags < 0 || n_indices < 0 || go_row_stride < dim) return PB200_EINVAL;
+    if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
+    if (n_bags == 0 || n_indices == 0) return PB200_OK;
+    const long long grid = (n_bags + 7) / 8;
+    if (grid > 0x7fffffffll) return PB200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mean = pool_mode == PB200_POOL_MEAN;
+    if (idx_type == PB200_IDX_I64)
+        embbag_bwd_sparse_values_kernel<long long><<<(unsigned)grid, 256, 0, st>>>(
+            grad_out, go_row_stride, dim, (const long long *)offsets, n_bags, include_last_offset ? 1 : 0,
+            n_indices, psw, mean, values);
+    else if (idx_type == PB200_IDX_I32)
+        embbag_bwd_sparse_values_kernel<int><<<(unsigned)grid, 256, 0, st>>>(
+            grad_out, go_row_stride, dim, (const int *)offsets, n_bags, include_last_offset ? 1 : 0, n_indices,
+            psw, mean, values);
+    else
+        return PB200_EINVAL;
+    count_launch();
+    PB200_LAUNCH_CHECK();
+    return PB200_OK;
 }

@@ -70,6 +70,12 @@ def _embedding_bag_backward(grad, indices, offsets, offset2bag, bag_size, maximu
         offsets = torch.cat([offsets.view(-1), offsets.new_tensor([indices.numel()])])
     elif offsets.numel() != n_bags + 1:
         raise PB200Error("param_b200 aten override: offsets do not match the gradient's bag count")
+    if sparse:
+        # aten::_embedding_bag_backward(sparse=True) returns an uncoalesced COO tensor with one entry per
+        # lookup (-> _embedding_bag_sparse_backward); same here, no dense [num_weights, dim] buffer
+        return _ops.embedding_bag_backward_sparse(grad.contiguous(), indices, offsets, int(num_weights),
+                                                  mode=_MODES[mode], per_sample_weights=per_sample_weights,
+                                                  include_last_offset=True)
     dst = torch.zeros((int(num_weights), dim), dtype=torch.float32, device=grad.device)
     if n_bags == 0 or indices.numel() == 0:
         return dst

@@ -400,6 +400,37 @@ def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tab
     _cabi.check(rc, "pb200_tbe_bwd_fused")
 
 
+def embedding_bag_backward_sparse(grad_out: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor,
+                                  num_rows: int, mode: str = "sum",
+                                  per_sample_weights: Optional[torch.Tensor] = None,
+                                  include_last_offset: bool = False) -> torch.Tensor:
+    """Gradient of a single-table EmbeddingBag as the uncoalesced sparse COO tensor nn.EmbeddingBag(sparse=True)
+    produces: indices = the lookup indices, values[i] = w_i * grad_out[bag(i)] (pb200_embbag_bwd_sparse).  No
+    dense [rows, dim] buffer is allocated."""
+    _need_cuda(grad_out, indices, offsets, per_sample_weights)
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    if grad_out.dtype != torch.float32 or grad_out.dim() != 2 or grad_out.stride(1) != 1:
+        raise PB200Error("grad_out must be fp32 [n_bags, dim] with unit inner stride")
+    n_bags = offsets.numel() - (1 if include_last_offset else 0)
+    if grad_out.shape[0] != n_bags:
+        raise PB200Error("grad_out must have one row per bag")
+    dim = int(grad_out.shape[1])
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+        if psw.numel() != indices.numel():
+            raise PB200Error("per_sample_weights must match indices")
+    values = torch.empty((indices.numel(), dim), dtype=torch.float32, device=grad_out.device)
+    if indices.numel():
+        rc = _cabi.load().pb200_embbag_bwd_sparse(grad_out.data_ptr(), grad_out.stride(0), dim, _ptr(offsets), n_bags,
+                                                  1 if include_last_offset else 0, indices.numel(), it, _ptr(psw),
+                                                  _MODE[mode], values.data_ptr(), _stream_ptr(grad_out))
+        _cabi.check(rc, "pb200_embbag_bwd_sparse")
+    return torch.sparse_coo_tensor(indices.to(torch.int64).view(1, -1), values, size=(int(num_rows), dim))
+
+
 def check_indices(row_offsets: torch.Tensor, num_tables: int, indices: torch.Tensor,
                   offsets: torch.Tensor, batch: int) -> int:
     """Debug-mode bounds check; returns the number of out-of-range lookups (synchronises)."""

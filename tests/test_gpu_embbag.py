@@ -382,3 +382,36 @@ def test_operator_plugin_runs(cuda_device, oracle):
     assert np.abs(op.op.weights.detach().cpu().numpy() - want).max() <= RTOL * np.abs(want).max()
     op.cleanup()
     assert op.op is None
+
+
+def test_sparse_gradient_matches_golden_and_allocates_no_dense_buffer(cuda_device, golden_dir):
+    """nn.EmbeddingBag(sparse=True) semantics (what the reference's alloc_embedding_tables builds,
+    pytorch_dist_backend.py:923-934): an uncoalesced COO gradient with one entry per lookup whose dense form is
+    the golden dW; the module returns it when constructed with sparse=True."""
+    from param_b200 import ops
+    from param_b200.compute.pt.pytorch_emb import B200EmbeddingBag
+    for k, c in _golden_cases(golden_dir):
+        rows, dim = c["weight"].shape
+        psw = None if c["psw"] is None else _t(c["psw"], cuda_device)
+        g = ops.embedding_bag_backward_sparse(_t(c["grad_out"], cuda_device), _t(c["indices"], cuda_device),
+                                              _t(c["offsets"], cuda_device), rows, mode=c["mode"],
+                                              per_sample_weights=psw)
+        assert g.is_sparse and g._nnz() == c["indices"].size and tuple(g.shape) == (rows, dim)
+        np.testing.assert_allclose(g.to_dense().cpu().numpy(), c["grad_weight"], rtol=RTOL, atol=1e-5,
+                                   err_msg=f"case {k}")
+        emb = B200EmbeddingBag(rows, dim, mode=c["mode"], sparse=True, _weight=_t(c["weight"], cuda_device))
+        out = emb(_t(c["indices"], cuda_device), _t(c["offsets"], cuda_device), psw)
+        out.backward(_t(c["grad_out"], cuda_device))
+        assert emb.weight.grad.is_sparse
+        np.testing.assert_allclose(emb.weight.grad.to_dense().cpu().numpy(), c["grad_weight"], rtol=RTOL, atol=1e-5)
+    # int32 indices, a dim that is not a multiple of 4 (scalar path), mean pooling
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, 50, size=200).astype(np.int32)
+    off = np.sort(rng.integers(0, 200, size=30)).astype(np.int32)
+    off[0] = 0
+    go = rng.standard_normal((30, 6)).astype(np.float32)
+    g = ops.embedding_bag_backward_sparse(_t(go, cuda_device), _t(idx, cuda_device), _t(off, cuda_device), 50, mode="mean")
+    ref = torch.nn.functional.embedding_bag(torch.from_numpy(idx.astype(np.int64)), w := torch.zeros(50, 6, requires_grad=True),
+                                            torch.from_numpy(off.astype(np.int64)), mode="mean")
+    ref.backward(torch.from_numpy(go))
+    np.testing.assert_allclose(g.to_dense().cpu().numpy(), w.grad.numpy(), rtol=RTOL, atol=1e-6)
