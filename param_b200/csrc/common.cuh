@@ -39,15 +39,6 @@ __device__ __forceinline__ float4 ld_row_f4(const float4 *p) {
                  : "l"(p));
     return v;
 }
-// Same read with an explicit L1 priority: rows at the head of a table (the popular ones under the reference's
-// Zipf generator) are kept, the rest does not allocate — the streaming cold rows stop evicting the hot ones.
-__device__ __forceinline__ float4 ld_row_f4_keep(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
-}
 // Streams read exactly once (indices, offsets, grad rows): do not pollute L1.
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
     float4 v;

@@ -25,8 +25,6 @@ struct FwdParams {
     int mean;
     int stage_cap;          // STAGED: index elements per stage buffer
     int weights_f16;        // table elements are __half (DIRECT variant only)
-    int head_rows;          // DIRECT, fp32: rows [0, head_rows) of every table keep L1 priority, the others
-                            // bypass L1 (0 = one policy for all rows)
 };
 
 template <typename index_t>
@@ -92,7 +90,7 @@ struct RowVec<__half> {
 // warp-uniform, every lane issues its loads unconditionally (lanes beyond dim/4 read column 0 and
 // drop the result at the store), and only groups shorter than the longest bag of the warp mask
 // their tail.  Per row and warp that is 1 SHFL + 1 IMAD.WIDE + 1 LDG.128 + 2 FADD2.
-template <typename index_t, int G, int C, bool WEIGHTED, int U, typename WT = float, bool HEAD = false>
+template <typename index_t, int G, int C, bool WEIGHTED, int U, typename WT = float>
 struct BagAccum {
     using V = typename RowVec<WT>::type;
     float4 acc[C];
@@ -103,8 +101,6 @@ struct BagAccum {
     }
 
     // N rows starting at lane j of the group; MASKED: rows at or beyond `valid` are dropped
-    unsigned head_end = 0;   // arena row below which a row of this group's table counts as "head" (0: off)
-
     template <int N, bool MASKED>
     __device__ __forceinline__ void batch(const V *const (&colp)[C], unsigned row_stride4,
                                           unsigned my_row, float my_w, int j, int valid) {
@@ -115,17 +111,8 @@ struct BagAccum {
             const unsigned row = __shfl_sync(0xffffffffu, my_row, j + u, G);
             if (WEIGHTED) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u, G);
             const unsigned long long roff = (unsigned long long)row * row_stride4;
-            if constexpr (HEAD) {
-                // uniform inside the lane group (one bag, one row); two predicated loads, same registers
-                const bool keep = row < head_end;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    v[u][c] = keep ? ld_row_f4_keep((const float4 *)(colp[c] + roff))
-                                   : ld_stream_f4((const float4 *)(colp[c] + roff));
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) v[u][c] = RowVec<WT>::ld(colp[c] + roff);
-            }
+            for (int c = 0; c < C; ++c) v[u][c] = RowVec<WT>::ld(colp[c] + roff);
         }
 #pragma unroll
         for (int u = 0; u < N; ++u) {

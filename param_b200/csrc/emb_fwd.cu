@@ -27,7 +27,7 @@ namespace pb200 {
 // ------------------------------------------------------------------------------------
 // DIRECT variant
 // ------------------------------------------------------------------------------------
-template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float, bool HEAD = false>
+template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float>
 __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     constexpr int BPW = 32 / G;  // bags per warp
     constexpr int U = UnrollFor<C>::value;
@@ -51,9 +51,8 @@ __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     const int minlen = (BPW == 1) ? len : __reduce_min_sync(0xffffffffu, len);
     const long long base_row = (active && p.table_row_offsets) ? p.table_row_offsets[t] : 0;
 
-    BagAccum<index_t, G, C, WEIGHTED, U, WT, HEAD> acc;
+    BagAccum<index_t, G, C, WEIGHTED, U, WT> acc;
     acc.zero();
-    if (HEAD) acc.head_end = (unsigned)base_row + (unsigned)p.head_rows;
     acc.template run<false>(p, (const index_t *)p.indices + begin,
                             WEIGHTED ? p.psw + begin : nullptr, base_row, len, minlen, maxlen,
                             lane_g, vec4);
@@ -63,11 +62,6 @@ __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
 template <typename index_t, int G, int C, bool WEIGHTED>
 __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) {
     tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
-}
-// head rows of every table keep L1 priority, cold rows bypass L1 (PB200_FWD_HEAD_ROWS, fp32, unweighted)
-template <typename index_t, int G, int C>
-__global__ void __launch_bounds__(256, 4) tbe_fwd_direct_head_kernel(const FwdParams p) {
-    tbe_fwd_direct_body<index_t, G, C, false, float, true>(p);
 }
 // same body compiled for 5 resident CTAs/SM (48 registers): selectable with PB200_FWD_OCC5=1
 template <typename index_t, int G, int C, bool WEIGHTED>
@@ -423,8 +417,6 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
             tbe_fwd_direct_f16_kernel<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (weighted)
             tbe_fwd_direct_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
-        else if (p.head_rows > 0 && p.table_row_offsets)
-            tbe_fwd_direct_head_kernel<index_t, G, C><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (occ5)
             tbe_fwd_direct_kernel_occ5<index_t, G, C, false><<<(unsigned)grid, 256, 0, st>>>(p);
         else
@@ -460,7 +452,8 @@ static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t
     // the head of every table staged into shared memory by cp.async.bulk was built and measured in round 2:
     // 4.30 ms with one contiguous bag range per CTA, 6.26 ms with all CTAs walking the tables in lockstep,
     // against 3.09 ms for DIRECT at 64 tables under Zipf 1.15 — profiles/r02f_ncu_fwd_hot_v1.md,
-    // r02h_*.log; removed.)
+    // r02h_*.log; removed.  So was an L1-priority split inside DIRECT — head rows ld ... L1::evict_last, the
+    // rest L1::no_allocate: 4.32 ms, the warm rows behind the head live on L1 too — profiles/r02i_head*.log.)
     if (algo == PB200_FWD_AUTO) algo = PB200_FWD_DIRECT;
     // bulk copies need 16 B-aligned index/offset arrays
     if ((((uintptr_t)p.indices | (uintptr_t)p.offsets) & 15) != 0) algo = PB200_FWD_DIRECT;
@@ -517,13 +510,6 @@ extern "C" int pb200_tbe_fwd(const float *weights, const int64_t *table_row_offs
     p.dim = dim;
     p.has_last_offset = 1;
     p.mean = pool_mode == PB200_POOL_MEAN;
-    {
-        static const int head_rows = [] {
-            const char *e = getenv("PB200_FWD_HEAD_ROWS");
-            return e ? atoi(e) : 0;
-        }();
-        p.head_rows = head_rows;
-    }
     cudaStream_t st = (cudaStream_t)stream;
     // Contract (param_b200.h): the arena holds fewer than 2^32 rows — arena row ids are 32-bit inside
     // the kernels.  table_row_offsets lives on the device, so the bound is the caller's to keep

@@ -380,8 +380,10 @@ def test_operator_plugin_runs(cuda_device, oracle):
     want = w0.astype(np.float64) + oracle.tbe_bwd(int(tro[-1]), tro, 128, idx.cpu().numpy(), off.cpu().numpy(), 64,
                                                   np.ones((64, 3 * 128), np.float32), scale=-0.1, dtype=np.float64)
     assert np.abs(op.op.weights.detach().cpu().numpy() - want).max() <= RTOL * np.abs(want).max()
-    op.cleanup()
-    assert op.op is None
+    op.cleanup()                    # outputs go, the built op stays (several inputs may run against one build)
+    assert op.fwd_out is None and op.grad_in is None and op.op is not None
+    out2 = op.forward(idx, off, w)
+    assert out2.shape == out.shape
 
 
 def test_sparse_gradient_matches_golden_and_allocates_no_dense_buffer(cuda_device, golden_dir):
