@@ -28,6 +28,9 @@ from ..._cabi import PB200Error
 # ---------------------------------------------------------------------------------------------
 # module
 # ---------------------------------------------------------------------------------------------
+_SPARSE_GRAD_MIN_ROWS_PER_LOOKUP = 8      # sparse=True returns a COO gradient when rows > 8 x lookups
+
+
 class _EmbeddingBagFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, indices, offsets, psw, mode, include_last_offset, fwd_algo, bwd_algo, sparse):
@@ -45,10 +48,13 @@ class _EmbeddingBagFn(torch.autograd.Function):
         dev = grad_out.device
         indices = indices.contiguous().view(-1)
         offsets = offsets.contiguous().view(-1)
-        if sparse:
+        if sparse and rows > _SPARSE_GRAD_MIN_ROWS_PER_LOOKUP * indices.numel():
             # nn.EmbeddingBag(sparse=True): an uncoalesced COO gradient with one entry per lookup — what the
             # reference's tables produce (pytorch_dist_backend.py:923-934) — instead of a dense zero-filled
-            # [rows, dim] buffer (5.1 GB for a 10 M x 128 table)
+            # [rows, dim] buffer (5.1 GB for a 10 M x 128 table).  When the table is NOT much larger than the
+            # batch's lookups the dense form is the cheaper one (autograd accumulates it in place, while COO
+            # gradients are concatenated step after step: 107 ms vs 57 ms per iteration under the reference's
+            # dlrm.py with 200 k-row tables, profiles/r02g_dlrm_*.log), so it is used there.
             g = ops.embedding_bag_backward_sparse(grad_out.contiguous(), indices, offsets, rows, mode=mode,
                                                   per_sample_weights=psw if weighted else None,
                                                   include_last_offset=include_last)

@@ -156,6 +156,32 @@ def run_et_replay(argv):
     et_replay.main()
 
 
+def run_trace_replay(argv):
+    """the reference's train/comms/pt/commsTraceReplay.py, unmodified, on a basic / ET / kineto trace.  Its
+    `"compute": "emb_lookup"` entries (commsTraceParser.py:137-147) call comms_utils.init_emb_lookup, which needs
+    fbgemm_gpu (comms_utils.py:1966-1979: logs an error and returns without it): the B200 set-up of the same
+    collectiveArgs fields (param_b200/comms/pt/emb_lookup.py) is put in its place, the replay loop is untouched."""
+    register()
+    from param_bench.train.comms.pt import comms_utils as ref_utils, commsTraceReplay
+
+    from ..comms.pt.emb_lookup import init_emb_lookup
+
+    ref_utils.init_emb_lookup = init_emb_lookup
+    # same start-up defect as dlrm.py (SURVEY appendix B): commsParamsHolderBase reads args.use_device_time, which
+    # only comms.py's parser defines (comms_utils.py:826)
+    orig = commsTraceReplay.commsTraceReplayBench.readArgs
+
+    def read_args(self, parser):
+        args = orig(self, parser)
+        if not hasattr(args, "use_device_time"):
+            args.use_device_time = False
+        return args
+
+    commsTraceReplay.commsTraceReplayBench.readArgs = read_args
+    sys.argv = ["commsTraceReplay.py"] + list(argv)
+    commsTraceReplay.main()
+
+
 def run_bench(argv):
     """the reference's train/compute/python/pytorch/run_benchmark.py with the B200 operator, input iterator and
     input-data generator registered (param_b200/compute/python_plugin.py) and _clear_cache taught sm_100"""
@@ -166,11 +192,24 @@ def run_bench(argv):
 
 def main():
     runners = {"comms": run_comms, "dlrm": run_dlrm, "emb": run_emb, "comm_replay": run_comm_replay,
-               "et_replay": run_et_replay, "bench": run_bench}
+               "et_replay": run_et_replay, "bench": run_bench, "trace_replay": run_trace_replay}
     if len(sys.argv) < 2 or sys.argv[1] not in runners:
-        raise SystemExit("usage: param_plugin {comms|dlrm|emb|comm_replay|et_replay|bench} <runner args>")
+        raise SystemExit("usage: param_plugin {comms|dlrm|emb|comm_replay|et_replay|bench|trace_replay} <runner args>")
     from . import refpath
     refpath.setup()
+    # evidence for the logs: how many libparam_b200 kernels this process launched under the reference's runner
+    import atexit
+
+    def _report():
+        try:
+            from .. import _cabi
+            if _cabi._lib is not None:
+                print(f"[param_plugin {sys.argv[0]}] libparam_b200 kernels launched by this process: "
+                      f"{_cabi.launch_count()}", flush=True)
+        except Exception:  # noqa: BLE001
+            pass
+
+    atexit.register(_report)
     runners[sys.argv[1]](sys.argv[2:])
 
 

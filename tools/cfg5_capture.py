@@ -78,15 +78,22 @@ def main():
     torch.manual_seed(1234 + rank)
     T_l, E, b, L = a.tables_per_rank, a.dim, a.local_batch, a.bag
     T_g, N = T_l * world, b * world
-    embs = nn.ModuleList([nn.EmbeddingBag(a.rows, E, mode="sum", sparse=True) for _ in range(T_l)]).to(dev)
+    # dense gradients: et_replay cannot allocate the sparse COO tensors a sparse=True table hands to autograd
+    # ("allocate tensor failed", et_replay.py:819); forward and the gradient scatter are the same ops either way
+    embs = nn.ModuleList([nn.EmbeddingBag(a.rows, E, mode="sum", sparse=False) for _ in range(T_l)]).to(dev)
     n_pairs = (T_g + 1) * T_g // 2
     top = nn.Linear(E + n_pairs, 1).to(dev)
     dense = torch.randn(b, E, device=dev)
     li, lj = torch.tril_indices(T_g + 1, T_g + 1, offset=-1)
-    li, lj = li.to(dev), lj.to(dev)
+    # the pairs as flat positions of the [T_g + 1, T_g + 1] interaction matrix: index_select instead of Z[:, li, lj],
+    # whose aten::index carries a None in its Tensor?[] argument that et_replay cannot rebuild (et_replay.py:1240)
+    tril_flat = (li * (T_g + 1) + lj).to(dev)
     # this rank's sparse inputs: LOCAL batch, ALL tables (table-major), fixed bag size
     my_idx = torch.randint(0, a.rows, (T_g * b * L,), device=dev)
     offsets = torch.arange(0, N * L, L, device=dev)                   # per table, global batch
+    # explicit unit per-sample weights: with None the backward node records an UNDEFINED tensor argument
+    # ("Tensor(nullptr (uninitialized))"), which et_replay cannot allocate (et_replay.py:819) and then cannot run
+    psw = torch.ones(N * L, device=dev)
     opt = torch.optim.SGD(list(embs.parameters()) + list(top.parameters()), lr=0.01)
 
     def step():
@@ -94,12 +101,12 @@ def main():
         recv = torch.empty(world * T_l * b * L, dtype=torch.int64, device=dev)
         dist.all_to_all_single(recv, my_idx, group=group)
         per_table = recv.view(world, T_l, b * L).permute(1, 0, 2).contiguous()      # [T_l, W * b * L]
-        ly = [embs[t](per_table[t].view(-1), offsets) for t in range(T_l)]            # T_l x [N, E]
+        ly = [embs[t](per_table[t].view(-1), offsets, per_sample_weights=psw) for t in range(T_l)]   # T_l x [N, E]
         pooled = torch.cat(ly, dim=1)                                                  # [N, T_l * E]
         out = _A2A.apply(pooled.view(-1), [b * T_l * E] * world, [b * T_l * E] * world, group)
         x = torch.cat([o.view(b, T_l * E) for o in out.split(b * T_l * E)], dim=1)   # [b, T_g * E]
         z = torch.cat([dense.view(b, 1, E), x.view(b, T_g, E)], dim=1)                # [b, T_g + 1, E]
-        zz = torch.bmm(z, z.transpose(1, 2))[:, li, lj]                               # interaction
+        zz = torch.index_select(torch.bmm(z, z.transpose(1, 2)).view(b, -1), 1, tril_flat)   # interaction
         loss = top(torch.cat([dense, zz], dim=1)).mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
