@@ -200,6 +200,17 @@ int pb200_embbag_bwd_sparse(const float *grad_out, int64_t go_row_stride, int32_
                             int64_t n_indices, int32_t idx_type, const float *psw, int32_t pool_mode,
                             float *values /* [n_indices, dim] */, void *stream);
 
+/* The segmented reduce of pb200_tbe_bwd(PB200_BWD_SORTED, plan_ready = 1) restricted to tables
+ * [table_lo, table_hi) of the request: the sorted range of those tables is read from `offsets` on the device
+ * (no host knowledge of lookup counts needed).  Lets the backward of a table group start as soon as ITS
+ * gradient columns have arrived (pb200_a2a_pooled_bwd_part).  The plan must have been built for the whole
+ * request (pb200_tbe_plan_build); unweighted or weighted, SUM or MEAN. */
+int pb200_tbe_bwd_tables(float *dst, const int64_t *table_row_offsets, int32_t num_tables, int32_t dim,
+                         const void *indices, int64_t n_indices, const void *offsets, int64_t batch,
+                         int32_t idx_type, const float *psw, int32_t pool_mode, const float *grad_out,
+                         int64_t go_stride_t, int64_t go_stride_b, float scale, int32_t table_lo,
+                         int32_t table_hi, void *plan, int64_t plan_bytes, void *stream);
+
 /* =========================================================================
  * 3b. Backward with the optimizer fused in ("exact": one update per touched row)
  * =========================================================================
@@ -344,6 +355,14 @@ int pb200_a2a_pooled_bwd(pb200_a2a_comm *comm, const float *grad /* [lN, T_globa
                          int32_t emb_dim, const int64_t *batch_split,
                          const int64_t *tables_split, int64_t out_window_off,
                          void *stream);
+
+/* The backward exchange in `parts` pieces: piece `part` moves, for every owner, the gradient columns of its tables
+ * [lo, hi) of that piece (tables split contiguously, remainder to the low pieces).  Same window layout as the
+ * whole exchange, one epoch per piece: the owner reduces piece g (pb200_tbe_bwd with table_lo / table_hi ... see
+ * pb200_tbe_bwd_tables) while piece g + 1 is still on the wire.  parts = 1 is pb200_a2a_pooled_bwd. */
+int pb200_a2a_pooled_bwd_part(pb200_a2a_comm *comm, const float *grad, int32_t emb_dim,
+                              const int64_t *batch_split, const int64_t *tables_split,
+                              int64_t out_window_off, int32_t part, int32_t parts, void *stream);
 
 /* Fused lookup + exchange, ONE kernel per rank: the batched EmbeddingBag forward over this
  * rank's tables for the GLOBAL batch (TBE request: offsets[T_local*N + 1]) whose epilogue stores

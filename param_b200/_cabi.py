@@ -18,11 +18,11 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libparam_b200.so"
 EXPORTED_SYMBOLS = (
     "pb200_abi_version", "pb200_error_string", "pb200_launch_count", "pb200_device_info",
     "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_tbe_fwd_f16", "pb200_check_indices",
-    "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd", "pb200_embbag_bwd_sparse",
+    "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd", "pb200_embbag_bwd_sparse", "pb200_tbe_bwd_tables",
     "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused", "pb200_tbe_plan_build",
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
     "pb200_a2a_comm_error", "pb200_a2a_single", "pb200_a2a_list",
-    "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_tbe_fwd_a2a",
+    "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_a2a_pooled_bwd_part", "pb200_tbe_fwd_a2a",
     "pb200_regroup_scratch_bytes", "pb200_regroup_sparse", "pb200_sparse_data_dist",
     "pb200_host_ctx_create", "pb200_host_ctx_destroy", "pb200_tbe_fwd_host", "pb200_tbe_step_host",
     "pb200_fill_uniform", "pb200_fill_zipf_indices",
@@ -94,6 +94,8 @@ def load():
     sig("pb200_tbe_bwd_scratch_bytes", i64, i64, i32, i64, i64, i32)
     sig("pb200_tbe_bwd", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64,
         f32, i32, i64, vp, i64, i32, vp)
+    sig("pb200_tbe_bwd_tables", C.c_int, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp, i64, i64, f32, i32, i32,
+        vp, i64, vp)
     sig("pb200_embbag_bwd_sparse", C.c_int, vp, i64, i32, vp, i64, i32, i64, i32, vp, i32, vp, vp)
     sig("pb200_tbe_bwd_fused_scratch_bytes", i64, i64, i32, i64, i32)
     sig("pb200_tbe_bwd_fused", C.c_int, vp, i32, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp,
@@ -108,6 +110,7 @@ def load():
     sig("pb200_a2a_list", C.c_int, vp, C.POINTER(vp), p_i64, p_i64, p_i64, C.POINTER(vp), vp)
     sig("pb200_a2a_pooled_fwd", C.c_int, vp, vp, i64, i64, i32, p_i64, p_i64, i64, vp)
     sig("pb200_a2a_pooled_bwd", C.c_int, vp, vp, i32, p_i64, p_i64, i64, vp)
+    sig("pb200_a2a_pooled_bwd_part", C.c_int, vp, vp, i32, p_i64, p_i64, i64, i32, i32, vp)
     sig("pb200_tbe_fwd_a2a", C.c_int, vp, vp, vp, i32, i32, vp, i64, vp, i32, i32, p_i64, p_i64, i64, vp)
     sig("pb200_regroup_scratch_bytes", i64, i32, i32, i64)
     sig("pb200_regroup_sparse", C.c_int, vp, vp, i64, i32, i32, i64, vp, vp, vp, vp, i64, vp)

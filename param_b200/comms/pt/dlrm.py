@@ -182,6 +182,10 @@ class DLRMParallelEmbedding:
         self._side = torch.cuda.Stream(device=device) if self.presort else None
         self._plan, self._plan_buf = None, None
         self.max_table_rows = max(rows) if rows else 0
+        # backward in pieces: the transpose exchange of table group g + 1 (comm stream) runs under the
+        # segmented reduce of group g (PB200_DLRM_BWD_PARTS, default 2; 1 = one exchange, then one reduce)
+        self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", "2")), min(self.tables_split)))
+        self._comm_stream = torch.cuda.Stream(device=device) if self.bwd_parts > 1 else None
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------
     def sparse_data_dist(self, batch: SparseBatch, device_side: Optional[bool] = None):
@@ -240,7 +244,28 @@ class DLRMParallelEmbedding:
     # ---- step 6: backward all-to-all + scatter-add ---------------------------------------------------
     def backward(self, grad: torch.Tensor) -> None:
         offsets, indices = self._saved
-        g_local = self.window.pooled_backward(grad.contiguous(), self.batch_split, self.tables_split,
+        grad = grad.contiguous()
+        if self.bwd_parts > 1 and self._plan is not None and not self._plan.exact:
+            # piece g of the exchange on the comm stream, its reduce on the caller's stream as soon as it has
+            # landed: only the first piece of the exchange is exposed
+            cur = torch.cuda.current_stream(self.device)
+            self._comm_stream.wait_stream(cur)                    # the gradient is ready on `cur`
+            grad.record_stream(self._comm_stream)
+            landed = []
+            for g in range(self.bwd_parts):
+                g_local = self.window.pooled_backward(grad, self.batch_split, self.tables_split, self.E,
+                                                      out_window_off=self.off_grad, stream=self._comm_stream,
+                                                      part=g, parts=self.bwd_parts)
+                ev = torch.cuda.Event()
+                ev.record(self._comm_stream)
+                landed.append(ev)
+            for g in range(self.bwd_parts):
+                cur.wait_event(landed[g])
+                lo, hi = ops.part_range(self.T_local, g, self.bwd_parts)
+                ops.tbe_backward_tables(self.arena.weights, self.arena.row_offsets, self.T_local, self.E, indices,
+                                        offsets, self.N, g_local, self._plan, lo, hi, layout="BTD", scale=-self.lr)
+            return
+        g_local = self.window.pooled_backward(grad, self.batch_split, self.tables_split,
                                               self.E, out_window_off=self.off_grad)
         ops.tbe_backward(self.arena.weights, self.arena.row_offsets, self.T_local, self.E, indices,
                          offsets, self.N, g_local, layout="BTD", scale=-self.lr, algo=self.bwd_algo,

@@ -355,16 +355,18 @@ class PeerWindow:
 
     def pooled_backward(self, grad: torch.Tensor, batch_split: Sequence[int],
                         tables_split: Sequence[int], emb_dim: int, out_window_off: int = 0,
-                        stream=None) -> torch.Tensor:
+                        stream=None, part: int = 0, parts: int = 1) -> torch.Tensor:
         """Transpose exchange (dlrm.py:180-218,137-154): grad [lN, T_global*E] -> this rank's
-        [N, T_local*E] gradient of its pooled lookups (a view of its window)."""
+        [N, T_local*E] gradient of its pooled lookups (a view of its window).  parts > 1: only the columns of
+        every owner's tables of piece `part` move (pb200_a2a_pooled_bwd_part); the returned view is the same
+        tensor, complete once all pieces have been exchanged."""
         lN, Tg, E = int(batch_split[self.rank]), int(sum(tables_split)), int(emb_dim)
         if grad.dtype != torch.float32 or not grad.is_contiguous() or grad.numel() != lN * Tg * E:
             raise PB200Error("grad must be contiguous fp32 [lN, T_global*E]")
-        rc = _cabi.load().pb200_a2a_pooled_bwd(self._comm, grad.data_ptr(), E,
-                                               _cabi.i64_array(batch_split), _cabi.i64_array(tables_split),
-                                               int(out_window_off), self._stream(stream))
-        _cabi.check(rc, "pb200_a2a_pooled_bwd")
+        rc = _cabi.load().pb200_a2a_pooled_bwd_part(self._comm, grad.data_ptr(), E,
+                                                    _cabi.i64_array(batch_split), _cabi.i64_array(tables_split),
+                                                    int(out_window_off), int(part), int(parts), self._stream(stream))
+        _cabi.check(rc, "pb200_a2a_pooled_bwd_part")
         N, T_l = int(sum(batch_split)), int(tables_split[self.rank])
         return self.view(out_window_off, N * T_l * E, torch.float32).view(N, T_l * E)
 

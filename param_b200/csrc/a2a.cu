@@ -571,11 +571,25 @@ extern "C" int pb200_a2a_pooled_fwd(pb200_a2a_comm *c, const float *in, int64_t 
     return a2a_launch_args(c, a, max_peer, (cudaStream_t)stream);
 }
 
+// tables [lo, hi) of a rank that owns n tables, for part `part` of `parts` (contiguous, remainder to the low parts)
+static void part_range(long long n, int part, int parts, long long &lo, long long &hi) {
+    const long long k = n / parts, m = n % parts;
+    lo = part * k + (part < m ? part : m);
+    hi = lo + k + (part < m ? 1 : 0);
+}
+
 extern "C" int pb200_a2a_pooled_bwd(pb200_a2a_comm *c, const float *grad, int32_t emb_dim,
                                     const int64_t *batch_split, const int64_t *tables_split,
                                     int64_t out_window_off, void *stream) {
+    return pb200_a2a_pooled_bwd_part(c, grad, emb_dim, batch_split, tables_split, out_window_off, 0, 1, stream);
+}
+
+extern "C" int pb200_a2a_pooled_bwd_part(pb200_a2a_comm *c, const float *grad, int32_t emb_dim,
+                                         const int64_t *batch_split, const int64_t *tables_split,
+                                         int64_t out_window_off, int32_t part, int32_t parts, void *stream) {
     if (!c || !grad || !batch_split || !tables_split || emb_dim < 1 || out_window_off < 0)
         return PB200_EINVAL;
+    if (parts < 1 || part < 0 || part >= parts) return PB200_EINVAL;
     const int W = c->world, me = c->rank;
     long long T_global = 0, table_base[PB200_A2A_MAX_RANKS], n_base[PB200_A2A_MAX_RANKS], N = 0;
     for (int r = 0; r < W; ++r) {
@@ -589,16 +603,22 @@ extern "C" int pb200_a2a_pooled_bwd(pb200_a2a_comm *c, const float *grad, int32_
     const long long T_local = tables_split[me];
     // my grad [lN_me, T_global*E]: owner j gets columns [table_base[j]*E, +T_j*E) of every row,
     // landing in its window as rows n_base[me] .. of a [N, T_j*E] tensor
+    // with parts > 1 only the columns of every owner's tables [lo, hi) of this part move: the owner can start
+    // reducing part g while part g + 1 is still on the wire (same layout in the window, same epoch protocol)
+    long long my_lo, my_hi;
+    part_range(T_local, part, parts, my_lo, my_hi);
     A2AArgs a{};
     long long max_peer = 0;
     for (int j = 0; j < W; ++j) {
-        a.copy[j].src = (const unsigned char *)(grad + table_base[j] * E);
+        long long lo, hi;
+        part_range(tables_split[j], part, parts, lo, hi);
+        a.copy[j].src = (const unsigned char *)(grad + (table_base[j] + lo) * E);
         a.copy[j].src_stride = T_global * E * 4;
         a.copy[j].dst_stride = tables_split[j] * E * 4;
-        a.copy[j].run_bytes = tables_split[j] * E * 4;
-        a.copy[j].rows = batch_split[me];
-        // source j's rows start at n_base[j] in MY [N, T_local*E] window tensor
-        a.recv_off[j] = out_window_off + n_base[j] * T_local * E * 4;
+        a.copy[j].run_bytes = (hi - lo) * E * 4;
+        a.copy[j].rows = (hi > lo) ? batch_split[me] : 0;
+        // source j's rows start at n_base[j] in MY [N, T_local*E] window tensor, my part's columns at my_lo
+        a.recv_off[j] = out_window_off + n_base[j] * T_local * E * 4 + my_lo * E * 4;
         const long long bytes = a.copy[j].run_bytes * a.copy[j].rows;
         if (bytes > max_peer) max_peer = bytes;
     }

@@ -186,10 +186,25 @@ __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long lon
     const int grp = lane / G;
     const int vec4 = p.dim >> 2;
     n = min(n, *p.n_dev);    // n is the host's capacity, the plan knows the count
+    long long lo = 0;
+    if (p.table_hi > p.table_lo) {
+        // a table group: its sorted positions are [off[table_lo * B], off[table_hi * B]) relative to off[0]
+        const long long a = (long long)p.table_lo * p.batch, b = (long long)p.table_hi * p.batch;
+        long long o0, oa, ob;
+        if (p.idx_is_i32) {
+            const int *off = (const int *)p.offsets;
+            o0 = off[0]; oa = off[a]; ob = off[b];
+        } else {
+            const long long *off = (const long long *)p.offsets;
+            o0 = off[0]; oa = off[a]; ob = off[b];
+        }
+        lo = oa - o0;
+        n = min(n, ob - o0);
+    }
     const long long seg = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + grp;
-    const long long s0 = seg * seg_len;
-    const long long s1 = min(s0 + (long long)seg_len, n);
-    const int my_n = (s0 < n) ? (int)(s1 - s0) : 0;
+    const long long s0 = max(seg * seg_len, lo);
+    const long long s1 = min((seg + 1) * (long long)seg_len, n);
+    const int my_n = (s0 < s1) ? (int)(s1 - s0) : 0;
     const int max_n = (BPW == 1) ? my_n : __reduce_max_sync(0xffffffffu, my_n);
 
     float4 *d4 = (float4 *)p.dst + (unsigned long long)chunk_row0 * (unsigned)vec4;
@@ -362,7 +377,8 @@ extern "C" int pb200_tbe_plan_build(void *scratch, int64_t scratch_bytes,
 namespace pb200 {
 
 static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows, void *scratch,
-                      long long scratch_bytes, bool plan_ready, cudaStream_t st) {
+                      long long scratch_bytes, bool plan_ready, cudaStream_t st, int table_lo = 0,
+                      int table_hi = 0) {
     const bool side = (p.psw != nullptr) || p.mean;
     const int seg_len = seg_len_from_env();
     static const int seg_occ4 = [] {
@@ -379,6 +395,9 @@ static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows
     const SortedView v = sorted_view(scratch, L, p.n_indices);
     BwdParams pr = p;
     pr.n_dev = v.count;
+    pr.table_lo = table_lo;
+    pr.table_hi = table_hi;
+    pr.idx_is_i32 = idx_type == PB200_IDX_I32;
     const int vec4 = p.dim >> 2;
     const long long n = v.n, n_seg = v.n_seg;
     // segmented reduce of the whole request: ONE launch (the keys are arena rows, globally sorted)
@@ -520,4 +539,38 @@ extern "C" int pb200_embbag_bwd_sparse(const float *grad_out, int64_t go_row_str
     count_launch();
     PB200_LAUNCH_CHECK();
     return PB200_OK;
+}
+
+extern "C" int pb200_tbe_bwd_tables(float *dst, const int64_t *table_row_offsets, int32_t num_tables,
+                                    int32_t dim, const void *indices, int64_t n_indices,
+                                    const void *offsets, int64_t batch, int32_t idx_type, const float *psw,
+                                    int32_t pool_mode, const float *grad_out, int64_t go_stride_t,
+                                    int64_t go_stride_b, float scale, int32_t table_lo, int32_t table_hi,
+                                    void *plan, int64_t plan_bytes, void *stream) {
+    if (!dst || !table_row_offsets || !offsets || !grad_out || !plan || (!indices && n_indices > 0))
+        return PB200_EINVAL;
+    if (num_tables < 1 || dim < 1 || batch < 0 || n_indices < 0) return PB200_EINVAL;
+    if (table_lo < 0 || table_hi > num_tables || table_hi < table_lo) return PB200_EINVAL;
+    if (pool_mode != PB200_POOL_SUM && pool_mode != PB200_POOL_MEAN) return PB200_EINVAL;
+    if (idx_type != PB200_IDX_I64 && idx_type != PB200_IDX_I32) return PB200_EINVAL;
+    if (dim % 4 != 0 || dim > 512) return PB200_EUNSUPPORTED;
+    if (((uintptr_t)dst & 15) || ((uintptr_t)grad_out & 15) || go_stride_t % 4 || go_stride_b % 4) return PB200_EALIGN;
+    if (table_hi == table_lo || batch == 0 || n_indices == 0) return PB200_OK;
+    BwdParams p{};
+    p.dst = dst;
+    p.table_row_offsets = (const long long *)table_row_offsets;
+    p.indices = indices;
+    p.offsets = offsets;
+    p.psw = psw;
+    p.grad_out = grad_out;
+    p.n_indices = n_indices;
+    p.batch = batch;
+    p.n_bags = (long long)num_tables * batch;
+    p.go_stride_t = go_stride_t;
+    p.go_stride_b = go_stride_b;
+    p.scale = scale;
+    p.num_tables = num_tables;
+    p.dim = dim;
+    p.mean = pool_mode == PB200_POOL_MEAN;
+    return bwd_sorted(p, idx_type, 0, plan, plan_bytes, /*plan_ready=*/true, (cudaStream_t)stream, table_lo, table_hi);
 }

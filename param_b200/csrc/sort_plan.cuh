@@ -149,6 +149,10 @@ struct BwdParams {
     // build.  n_indices is the host's value and may be a capacity (a device-side redistribution hands over
     // an indices buffer whose valid prefix only the device knows): the reducers use min(n_indices, *n_dev).
     const long long *n_dev;
+    // SORTED reduce of a table group: only sorted positions in [offsets[table_lo * batch], offsets[table_hi *
+    // batch]) - offsets[0] are reduced (read on the device); table_hi <= table_lo: the whole request
+    int table_lo, table_hi;
+    int idx_is_i32;
 };
 
 // Builds the plan in `plan` (layout above) on `st`.  Returns a PB200 code; never synchronises.

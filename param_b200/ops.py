@@ -342,6 +342,46 @@ def tbe_backward(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, 
     _cabi.check(rc, "pb200_tbe_bwd")
 
 
+def part_range(n: int, part: int, parts: int):
+    """tables [lo, hi) of piece `part` when n tables are cut into `parts` contiguous pieces (remainder to the low
+    pieces) — the split pb200_a2a_pooled_bwd_part uses"""
+    k, m = divmod(int(n), int(parts))
+    lo = part * k + min(part, m)
+    return lo, lo + k + (1 if part < m else 0)
+
+
+def tbe_backward_tables(dst: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, dim: int,
+                        indices: torch.Tensor, offsets: torch.Tensor, batch: int, grad_out: torch.Tensor,
+                        plan: SortPlan, table_lo: int, table_hi: int, layout: str = "BTD", scale: float = 1.0,
+                        mode: str = "sum", per_sample_weights: Optional[torch.Tensor] = None) -> None:
+    """The segmented reduce of tbe_backward(algo="sorted", plan=plan) for tables [table_lo, table_hi) only
+    (pb200_tbe_bwd_tables): the backward of a table group can start when ITS gradient columns have arrived."""
+    _need_cuda(dst, row_offsets, indices, offsets, grad_out, per_sample_weights)
+    indices = indices.contiguous().view(-1)
+    offsets = offsets.contiguous().view(-1)
+    it = _idx_type(indices, offsets)
+    T, D = num_tables, dim
+    if offsets.numel() != T * batch + 1:
+        raise PB200Error("offsets must have T*batch+1 entries")
+    if grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.numel() != T * batch * D:
+        raise PB200Error("grad_out must be contiguous fp32 with T*batch*dim elements")
+    if dst.dtype != torch.float32 or dst.dim() != 2 or dst.shape[1] != D or not dst.is_contiguous():
+        raise PB200Error("dst must be a contiguous fp32 [rows, dim] tensor")
+    if plan.exact:
+        raise PB200Error("table-range backward runs on a SORTED plan (exact=False)")
+    st_t, st_b = _layout_strides(layout, T, D, batch)
+    psw = None
+    if per_sample_weights is not None:
+        psw = per_sample_weights.contiguous().view(-1).to(torch.float32)
+    lib = _cabi.load()
+    nbytes = int(lib.pb200_tbe_bwd_scratch_bytes(indices.numel(), T, batch, dst.shape[0], BWD_SORTED))
+    ptr = _use_plan(plan, _plan_signature(indices, offsets, T, D, batch, layout, mode, psw), nbytes, dst.device)
+    rc = lib.pb200_tbe_bwd_tables(dst.data_ptr(), row_offsets.data_ptr(), T, D, _ptr(indices), indices.numel(),
+                                  _ptr(offsets), batch, it, _ptr(psw), _MODE[mode], grad_out.data_ptr(), st_t, st_b,
+                                  float(scale), int(table_lo), int(table_hi), ptr, nbytes, _stream_ptr(dst))
+    _cabi.check(rc, "pb200_tbe_bwd_tables")
+
+
 def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tables: int, dim: int,
                        indices: torch.Tensor, offsets: torch.Tensor, batch: int,
                        grad_out: torch.Tensor, optimizer: str = "exact_sgd", lr: float = 0.01,

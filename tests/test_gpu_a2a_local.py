@@ -307,3 +307,25 @@ def test_all_to_all_single_counts_splits_along_dim0(cuda_device, oracle):
     from param_b200._cabi import PB200Error
     with pytest.raises(PB200Error):     # output too small for what the splits deliver
         grp.windows[0].all_to_all_single(torch.empty((2, 6), device=cuda_device), ins[0], [3, 2], [3, 5])
+
+
+@pytest.mark.parametrize("W,T,parts", [(2, 7, 2), (4, 9, 3), (3, 4, 4)])
+def test_pooled_backward_in_pieces_equals_whole(cuda_device, oracle, W, T, parts):
+    """pb200_a2a_pooled_bwd_part: the transpose exchange cut into table groups (so that the reduce of group g can
+    run under the exchange of group g + 1) lands exactly what the single exchange lands — also when a rank owns
+    fewer tables than there are pieces (empty pieces)."""
+    from param_b200.comms.pt.dlrm import split_lengths
+    N, E = 40, 32
+    ts, bs = split_lengths(T, W), split_lengths(N, W)
+    rng = np.random.default_rng(W * 100 + T)
+    grads_h = [rng.standard_normal((bs[r], T * E)).astype(np.float32) for r in range(W)]
+    want = oracle.pooled_a2a_bwd(grads_h, bs, ts, E)
+    grads = [torch.from_numpy(g).to(cuda_device) for g in grads_h]
+    grp = _group(W, 8 << 20, cuda_device)
+    for w in grp.windows:
+        w.view(0, 1 << 20, torch.float32).fill_(float("nan"))
+    for g in range(parts):
+        gins = _run_all(grp, lambda r, w, st: w.pooled_backward(grads[r], bs, ts, E, stream=st, part=g, parts=parts))
+    for r in range(W):
+        got = gins[r].view(N, ts[r], E).permute(1, 0, 2).cpu().numpy()
+        assert np.array_equal(got, want[r]), r

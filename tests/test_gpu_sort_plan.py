@@ -184,3 +184,30 @@ def test_plan_fixed_size_bags(cuda_device, bag):
     k, v, _, _ = _plan_arrays(plan, idx.size)
     assert np.array_equal(k, keys)
     assert np.array_equal(v, goff[order])
+
+
+def test_backward_by_table_groups_equals_whole(cuda_device, oracle):
+    """pb200_tbe_bwd_tables: the segmented reduce restricted to table groups (position ranges read from the
+    offsets on the device; groups cut segments anywhere) — all groups together equal the whole backward and the
+    float64 oracle, each group alone touches only its tables' rows."""
+    from param_b200 import ops
+    rows, B, D = [3000, 50, 7000, 900, 12], 700, 64
+    rng = np.random.default_rng(77)
+    offsets, idx = _request(rng, rows, B, 15, alpha=1.1)
+    T = len(rows)
+    tro_h = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    tro, i_d, o_d = _t(tro_h, cuda_device), _t(idx, cuda_device), _t(offsets, cuda_device)
+    g = torch.randn(B, T * D, device=cuda_device)
+    ref64 = oracle.tbe_bwd(int(tro_h[-1]), tro_h, D, idx, offsets, B, g.cpu().numpy(), dtype=np.float64)
+    plan = ops.tbe_plan(tro, T, D, i_d, o_d, B, max(rows))
+    dst = torch.zeros((int(tro_h[-1]), D), device=cuda_device)
+    for parts in (1, 2, 3):
+        dst.zero_()
+        for p_ in range(parts):
+            lo, hi = ops.part_range(T, p_, parts)
+            before = dst.clone()
+            ops.tbe_backward_tables(dst, tro, T, D, i_d, o_d, B, g, plan, lo, hi)
+            changed = (dst != before).any(dim=1).nonzero().view(-1)
+            if changed.numel():
+                assert int(changed.min()) >= tro_h[lo] and int(changed.max()) < tro_h[hi], (parts, p_)
+        assert np.abs(dst.cpu().numpy() - ref64).max() <= 1e-5 * np.abs(ref64).max(), parts
