@@ -161,10 +161,15 @@ def run_trace_replay(argv):
     `"compute": "emb_lookup"` entries (commsTraceParser.py:137-147) call comms_utils.init_emb_lookup, which needs
     fbgemm_gpu (comms_utils.py:1966-1979: logs an error and returns without it): the B200 set-up of the same
     collectiveArgs fields (param_b200/comms/pt/emb_lookup.py) is put in its place, the replay loop is untouched."""
-    register()
-    from param_bench.train.comms.pt import comms_utils as ref_utils, commsTraceReplay
+    cls = register()
+    from param_bench.train.comms.pt import comms_utils as ref_utils, commsTraceReplay, pytorch_dist_backend
 
     from ..comms.pt.emb_lookup import init_emb_lookup
+
+    if "b200" in argv:
+        # initBackend constructs PyTorchDistBackend by name for --nw-stack pytorch-dist (commsTraceReplay.py:
+        # 1311-1316, no plugin registry there): hand it the subclass
+        pytorch_dist_backend.PyTorchDistBackend = cls
 
     ref_utils.init_emb_lookup = init_emb_lookup
     # same start-up defect as dlrm.py (SURVEY appendix B): commsParamsHolderBase reads args.use_device_time, which
