@@ -184,7 +184,11 @@ class DLRMParallelEmbedding:
         self.max_table_rows = max(rows) if rows else 0
         # backward in pieces: the transpose exchange of table group g + 1 (comm stream) runs under the
         # segmented reduce of group g (PB200_DLRM_BWD_PARTS, default 2; 1 = one exchange, then one reduce)
-        self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", "2")), min(self.tables_split)))
+        # measured at N = 2 (profiles/r02l_bench_n2*.log): 2 pieces cost 5 % there (3.01 vs 2.86 ms: the exchange is
+        # 0.48 ms, less than what the second epoch + launch costs), so pieces are the default from 4 ranks on,
+        # where the exchange is 1.3 - 2.8 ms
+        default_parts = "2" if self.world >= 4 else "1"
+        self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", default_parts)), min(self.tables_split)))
         self._comm_stream = torch.cuda.Stream(device=device) if self.bwd_parts > 1 else None
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------

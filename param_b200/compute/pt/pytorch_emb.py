@@ -60,10 +60,10 @@ class _EmbeddingBagFn(torch.autograd.Function):
                                                   include_last_offset=include_last)
             return g, None, None, None, None, None, None, None, None
         if not include_last:  # the batched kernel wants B+1 offsets
-            offsets = torch.cat([offsets, torch.tensor([indices.numel()], dtype=offsets.dtype, device=dev)])
+            offsets = ops.close_offsets(offsets, indices.numel())
         n_bags = offsets.numel() - 1
         grad_w = torch.zeros((rows, dim), dtype=torch.float32, device=dev)
-        row_off = torch.tensor([0, rows], dtype=torch.int64, device=dev)
+        row_off = ops.single_table_row_offsets(rows, dev)
         ops.tbe_backward(grad_w, row_off, 1, dim, indices, offsets, n_bags, grad_out.contiguous(),
                          layout="TBD", scale=1.0, mode=mode,
                          per_sample_weights=psw if weighted else None, algo=bwd_algo)

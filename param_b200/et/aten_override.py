@@ -67,7 +67,7 @@ def _embedding_bag_backward(grad, indices, offsets, offset2bag, bag_size, maximu
     # nn.EmbeddingBag offsets hold n_bags entries (n_bags + 1 with include_last_offset); the batched
     # kernel takes the closed form with the trailing end offset
     if offsets.numel() == n_bags:
-        offsets = torch.cat([offsets.view(-1), offsets.new_tensor([indices.numel()])])
+        offsets = _ops.close_offsets(offsets, indices.numel())
     elif offsets.numel() != n_bags + 1:
         raise PB200Error("param_b200 aten override: offsets do not match the gradient's bag count")
     if sparse:
@@ -79,7 +79,7 @@ def _embedding_bag_backward(grad, indices, offsets, offset2bag, bag_size, maximu
     dst = torch.zeros((int(num_weights), dim), dtype=torch.float32, device=grad.device)
     if n_bags == 0 or indices.numel() == 0:
         return dst
-    row_offsets = torch.tensor([0, int(num_weights)], dtype=torch.int64, device=grad.device)
+    row_offsets = _ops.single_table_row_offsets(int(num_weights), grad.device)
     _ops.tbe_backward(dst, row_offsets, 1, dim, indices, offsets, n_bags, grad.contiguous(), layout="TBD",
                       scale=1.0, mode=_MODES[mode], per_sample_weights=per_sample_weights, algo="auto")
     return dst

@@ -440,6 +440,27 @@ def tbe_backward_fused(weights: torch.Tensor, row_offsets: torch.Tensor, num_tab
     _cabi.check(rc, "pb200_tbe_bwd_fused")
 
 
+_row_offsets_cache: dict = {}
+
+
+def single_table_row_offsets(num_rows: int, device) -> torch.Tensor:
+    """int64 [0, num_rows] on `device`, cached: building it from a Python list on every backward is a
+    synchronising H2D copy (it cost the aten override 370 us per op under et_replay, profiles/r02l_*)."""
+    key = (int(num_rows), device.type, device.index)
+    t = _row_offsets_cache.get(key)
+    if t is None:
+        t = torch.tensor([0, int(num_rows)], dtype=torch.int64, device=device)
+        _row_offsets_cache[key] = t
+    return t
+
+
+def close_offsets(offsets: torch.Tensor, n_indices: int) -> torch.Tensor:
+    """nn.EmbeddingBag offsets (one per bag) -> the closed form with the trailing end offset, built on the device
+    (new_full is a fill kernel: no host-to-device copy, no synchronisation)"""
+    offsets = offsets.view(-1)
+    return torch.cat([offsets, offsets.new_full((1,), int(n_indices))])
+
+
 def embedding_bag_backward_sparse(grad_out: torch.Tensor, indices: torch.Tensor, offsets: torch.Tensor,
                                   num_rows: int, mode: str = "sum",
                                   per_sample_weights: Optional[torch.Tensor] = None,
