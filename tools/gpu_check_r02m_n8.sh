@@ -18,6 +18,9 @@ done
 DLRM="--device cuda --mini-batch-size 4096 --arch-embedding-size $(python -c "print('-'.join(['500000']*128))") --arch-sparse-feature-size 128 --num-indices-per-lookup 20 --num-indices-per-lookup-fixed True --num-batches 8 --warmup-batches 2"
 PB200_PLUGIN_BACKEND=stock run dlrm_stock $TR --master-port 29706 -m -- param_b200.integration.param_plugin dlrm --backend nccl $DLRM
 run dlrm_b200 $TR --master-port 29707 -m -- param_b200.integration.param_plugin dlrm --backend nccl $DLRM
+python tools/make_basic_trace.py --world 8 --out $O/dlrm_step_basic_w8.json > /dev/null
+run trace_replay_b200 $TR --master-port 29712 -m -- param_b200.integration.param_plugin trace_replay \
+      --trace-path $O/dlrm_step_basic_w8.json --trace-type basic --backend b200 --device cuda --num-replays 3
 run cfg5_capture $TR --master-port 29708 tools/cfg5_capture.py --out $O/cfg5_trace_n8 --tables-per-rank 8 --rows 500000 --dim 128 --local-batch 4096 --bag 20
 for be in nccl b200; do
   run cfg5_comm_replay_$be $TR --master-port 29709 -m -- param_b200.integration.param_plugin comm_replay --trace-type et \
