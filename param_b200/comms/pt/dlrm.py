@@ -13,7 +13,9 @@ Table-parallel embeddings + batch-parallel dense part, joined by an all-to-all (
                                                             into the peers' final [lN, T_g*E] tensors
   tempB.backward(C) -> a2a bwd + cat/split +             pb200_a2a_pooled_bwd + pb200_tbe_bwd scatter-add
     EmbeddingBagBackward (:1296, :180-218, :137-154)
-  MLP-gradient all_reduce (:1266-1281, :1303-1317)       stays on NCCL (dist.all_reduce), out of scope
+  MLP-gradient all_reduce (:1266-1281, :1303-1317)       the runner's two stages: async dist.all_reduce (NCCL) per
+                                                            layer tensor, closed by a barrier — pass-through
+  timers / report (:880-1009, :1011-1193)                 MARKS / REGIONS: the same 21 rows, same table layout
 
 Run:  torchrun --nproc-per-node 8 -m param_b200.comms.pt.dlrm --mini-batch-size 8192 \
           --arch-embedding-size 1000000x512 --arch-sparse-feature-size 128 --num-indices-per-lookup 20
@@ -192,12 +194,14 @@ class DLRMParallelEmbedding:
         self._comm_stream = torch.cuda.Stream(device=device) if self.bwd_parts > 1 else None
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------
-    def sparse_data_dist(self, batch: SparseBatch, device_side: Optional[bool] = None):
+    def sparse_data_dist(self, batch: SparseBatch, device_side: Optional[bool] = None, mark=None):
         """batch-parallel -> table-parallel redistribution of (lengths, indices); returns the TBE
         request (offsets int64[T_l*N+1], indices) for this rank's tables over the GLOBAL batch.
         device_side=True (default): one asynchronous call, index counts never leave the device
         (the returned indices tensor then has the window's capacity; offsets[-1] entries are valid).
-        device_side=False: the two-collective form with ONE [2, W]-count D2H in between."""
+        device_side=False: the two-collective form with ONE [2, W]-count D2H in between; `mark(name)` is
+        then called at the reference's offset_xchg_end / idx_xchg_start / idx_xchg_end stamps (dlrm.py:786-830)."""
+        mark = mark or (lambda name: None)
         W, b, win = self.world, self.b, self.window
         if batch.count != self.T_global or batch.batch_size != b:
             raise PB200Error("SparseBatch does not match the configured tables / local batch")
@@ -211,6 +215,7 @@ class DLRMParallelEmbedding:
         in_splits, out_splits = lengths_exchange_splits(self.tables_split, self.rank, b)
         lengths_out = win.all_to_all_single(None, batch.lengths, out_splits, in_splits,
                                             out_window_off=self.off_lengths)
+        mark("offset_xchg_end")
         # element counts per destination / per source: the one host round trip (the reference has
         # .item() + two .numpy() here, dlrm.py:801-818)
         send_counts, recv_counts = indices_exchange_counts(batch.lengths, lengths_out,
@@ -220,17 +225,22 @@ class DLRMParallelEmbedding:
         n_recv = int(sum(idx_out))
         if n_recv > self.cap_indices:
             raise PB200Error("received more indices than the window was sized for (raise max_bag)")
+        mark("idx_xchg_start")
         indices_out = win.all_to_all_single(None, batch.indices, idx_out, idx_in,
                                             out_window_off=self.off_indices)
+        mark("idx_xchg_end")
         # per-table regroup + offsets (splitPerTable / lengthsToOffsets, dlrm.py:430-504, 245-251)
         _, offsets, indices = ops.regroup_sparse(lengths_out, indices_out[:n_recv], W, self.T_local, b)
         return offsets, indices
 
     # ---- steps 3+4: apply_emb + forward all-to-all ------------------------------------------------
-    def forward(self, offsets: torch.Tensor, indices: torch.Tensor, fused: Optional[bool] = None) -> torch.Tensor:
+    def forward(self, offsets: torch.Tensor, indices: torch.Tensor, fused: Optional[bool] = None,
+                before_exchange=None) -> torch.Tensor:
         """lookup for the global batch + exchange; returns [lN, T_global*E].  fused=True (default):
         ONE kernel whose epilogue stores pooled rows into the peers' windows (pb200_tbe_fwd_a2a);
-        fused=False: lookup kernel to a local [N, T_l*E] buffer, then the push kernel."""
+        fused=False: lookup kernel to a local [N, T_l*E] buffer, then the push kernel.
+        before_exchange: called where the reference stamps fwd_a2a_start (after apply_emb is queued, before the
+        all-to-all, dlrm.py:1239-1253) — with the fused kernel that is before the one launch."""
         self._saved = (offsets, indices)
         self._plan = None
         if self.presort:
@@ -239,9 +249,13 @@ class DLRMParallelEmbedding:
                                       stream=self._side, buf=self._plan_buf)
             self._plan_buf = self._plan.buf
         if self.fused if fused is None else fused:
+            if before_exchange is not None:
+                before_exchange()
             return self.window.lookup_forward_fused(self.arena, indices, offsets, self.batch_split,
                                                     self.tables_split, out_window_off=self.off_pooled)
         ops.tbe_forward(self.arena, indices, offsets, self.N, layout="BTD", out=self._pooled_local)
+        if before_exchange is not None:
+            before_exchange()
         return self.window.pooled_forward(self._pooled_local, self.batch_split, self.tables_split, self.E,
                                           layout="BTD", out_window_off=self.off_pooled)
 
@@ -308,8 +322,111 @@ class NCCLReferenceEmbedding:
 
 
 # ------------------------------------------------------------------------------------------------
-# runner
+# runner: the reference's iteration, marks and report table (dlrm.py:880-1009, 1011-1193, 1200-1323)
 # ------------------------------------------------------------------------------------------------
+# Host-clock marks of one iteration, in the order they are taken.  As in the reference they are wall-clock
+# stamps; the device is drained only where the reference calls sync_barrier (before bef_emb_lookup, after
+# grad_push_start, after each all-reduce stage) — or at every mark with --perf-debug.
+MARKS = ("iter_start", "length_calc_end", "mem_push_idx_end", "offset_xchg_start", "offset_xchg_end",
+         "idx_xchg_start", "idx_xchg_end", "bef_emb_lookup", "fwd_a2a_start", "fwd_a2a_end", "grad_push_start",
+         "bwd_top_ar_start", "bwd_top_ar_end", "bwd_a2a_start", "bwd_a2a_end", "bwd_bot_ar_start", "bwd_bot_ar_end")
+
+# (region, first mark, last mark) — the 21 rows of the reference's table, same names and order
+# (initTimers dlrm.py:961-1009, all_timers dlrm.py:1015-1037)
+REGIONS = (
+    ("intermed_calc_length", "iter_start", "length_calc_end"),
+    ("mem_push_idx", "length_calc_end", "mem_push_idx_end"),
+    ("intermed_bef_offset_xchg", "mem_push_idx_end", "offset_xchg_start"),
+    ("offset_xchg", "offset_xchg_start", "offset_xchg_end"),
+    ("intermed_btw_offset_idx_xchg", "offset_xchg_end", "idx_xchg_start"),
+    ("idx_xchg", "idx_xchg_start", "idx_xchg_end"),
+    ("intermed_post_idx_xchg_sparse_dist", "idx_xchg_end", "bef_emb_lookup"),
+    ("intermed_emb_lookup_to_a2a_start", "bef_emb_lookup", "fwd_a2a_start"),
+    ("fwd_a2a", "fwd_a2a_start", "fwd_a2a_end"),
+    ("intermed_fwd_a2a_grad_push", "fwd_a2a_end", "grad_push_start"),
+    ("mem_push_gradients", "grad_push_start", "bwd_top_ar_start"),
+    ("bwd_top_ar", "bwd_top_ar_start", "bwd_top_ar_end"),
+    ("intermed_top_ar_end_to_bwd_a2a_start", "bwd_top_ar_end", "bwd_a2a_start"),
+    ("bwd_a2a", "bwd_a2a_start", "bwd_a2a_end"),
+    ("intermed_bwd_a2a_bot_ar", "bwd_a2a_end", "bwd_bot_ar_start"),
+    ("bwd_bot_ar", "bwd_bot_ar_start", "bwd_bot_ar_end"),
+    ("iter_time", "iter_start", "bwd_bot_ar_end"),
+    ("iter_data_prep", "iter_start", "bef_emb_lookup"),
+    ("iter_fwd_a2a", "iter_start", "grad_push_start"),
+    ("iter_bwd_top_ar", "iter_start", "bwd_top_ar_end"),
+    ("iter_bwd_a2a", "iter_start", "bwd_bot_ar_start"),
+)
+# regions that carry a message size in the table; every other row reports 0 (intermed_region_memory, dlrm.py:912-934)
+SIZED_REGIONS = ("offset_xchg", "idx_xchg", "fwd_a2a", "bwd_top_ar", "bwd_a2a", "bwd_bot_ar")
+
+
+def mlp_layer_shapes(spec: Sequence[int]) -> List[List[int]]:
+    """'a-b-c' -> [[b, a], [c, b]]: one [out, in] weight per consecutive pair (create_mlp, dlrm.py:400-411)."""
+    dims = [int(v) for v in spec]
+    return [[dims[i + 1], dims[i]] for i in range(len(dims) - 1)]
+
+
+def top_mlp_dims(n_tables: int, bot: Sequence[int], top: Sequence[int], interaction_op: str = "dot",
+                 interaction_itself: bool = False, project_size: int = 0) -> List[int]:
+    """Input width of the top MLP from the interaction (dlrm.py:575-604): with F = tables + 1 features and
+    d = last bottom width, 'dot' gives F(F-1)/2 + d pairs (F(F+1)/2 + d with the diagonal), 'cat' gives F*d;
+    a projection replaces it by F*project_size + d."""
+    F, d = int(n_tables) + 1, int(bot[-1])
+    if interaction_op == "dot":
+        n_int = (F * (F + 1)) // 2 + d if interaction_itself else (F * (F - 1)) // 2 + d
+    elif interaction_op == "cat":
+        n_int = F * d
+    else:
+        raise PB200Error(f"--arch-interaction-op={interaction_op} is not supported")
+    if project_size > 0:
+        n_int = F * int(project_size) + d
+    return [n_int] + [int(v) for v in top]
+
+
+def region_times_us(marks: dict) -> dict:
+    """One iteration's region latencies in microseconds from its marks (computeTimes, dlrm.py:952-959; the
+    reference labels the same quantity 'nanoseconds' and prints it under 'Latency(us)')."""
+    return {name: (marks[b] - marks[a]) * 1e6 for name, a, b in REGIONS}
+
+
+def percentile_rows(lat: "torch.Tensor", mem: "torch.Tensor"):
+    """lat, mem: [W, R, iters] gathered samples.  Returns (per_sample_rows, per_rank_mean_rows), each a list of
+    (region, mem_p50, min, p50, p75, p95, running sum of p50 over the non-'iter' regions) — the two tables the
+    reference prints (dlrm.py:1086-1160): percentiles over all W*iters samples, and over the W per-rank means."""
+    import numpy as np
+    W, R, _ = lat.shape
+    rows_all, rows_mean, run_all, run_mean = [], [], 0.0, 0.0
+    for r in range(R):
+        name = REGIONS[r][0]
+        samples = lat[:, r, :].reshape(-1).numpy()
+        means = lat[:, r, :].mean(dim=1).numpy()
+        mem_p50 = float(np.percentile(mem[:, r, :].reshape(-1).numpy(), 50))
+        pa = [float(np.percentile(samples, q)) for q in (50, 75, 95)]
+        pm = [float(np.percentile(means, q)) for q in (50, 75, 95)]
+        if "iter" not in name:
+            run_all += pa[0]
+            run_mean += pm[0]
+        rows_all.append((name, mem_p50, float(samples.min()), *pa, run_all))
+        rows_mean.append((name, mem_p50, float(means.min()), *pm, run_mean))
+    return rows_all, rows_mean
+
+
+def format_report(iters: int, rows) -> str:
+    """The reference's table layout (dlrm.py:1069-1081, 1133-1177): tab-separated, a blank line before the
+    iter_* rows, a total_time footer."""
+    out = ["\t{}\t{:>36}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}".format(
+        "iters", "region", "memory (B)", "Latency(us):min", "p50", "p75", "p95", "sum(p50)")]
+    total = 0.0
+    for name, mem, lo, p50, p75, p95, run in rows:
+        if name == "iter_time":
+            out.append("\n")
+        out.append("\t%d\t%36s\t%12s\t%12s\t%12s\t%12s\t%12s\t%12s"
+                   % (iters, name, "%d" % mem, "%.3f" % lo, "%.3f" % p50, "%.3f" % p75, "%.3f" % p95, "%.3f" % run))
+        total = run
+    out.append("\t%d\t%36s\t%12s\t%12s\t%12s" % (iters, "total_time", "N/A", "N/A", "%.3f" % total))
+    return "\n".join(out)
+
+
 def _parse(argv=None):
     ap = argparse.ArgumentParser(description="DLRM comm pattern on B200 peer-push all-to-all")
     ap.add_argument("--mini-batch-size", type=int, default=8192, help="per-rank batch")
@@ -317,16 +434,28 @@ def _parse(argv=None):
     ap.add_argument("--warmup-batches", type=int, default=3)
     ap.add_argument("--arch-embedding-size", type=str, default="100000x16")
     ap.add_argument("--arch-sparse-feature-size", type=int, default=128)
+    ap.add_argument("--arch-mlp-bot", type=str, default="4-3-2")
+    ap.add_argument("--arch-mlp-top", type=str, default="4-2-1")
+    ap.add_argument("--arch-interaction-op", type=str, default="dot")
+    ap.add_argument("--arch-interaction-itself", action="store_true")
+    ap.add_argument("--arch-project-size", type=int, default=0)
     ap.add_argument("--num-indices-per-lookup", type=int, default=20)
     ap.add_argument("--num-indices-per-lookup-fixed", type=lambda s: str(s).lower() in ("1", "true"), default=True)
     ap.add_argument("--alpha", type=float, default=0.0)
     ap.add_argument("--lr", type=float, default=0.0)
+    ap.add_argument("--perf-debug", action="store_true", help="drain the device at every mark (dlrm.py:1261-1299)")
+    ap.add_argument("--two-collective-dist", action="store_true",
+                    help="lengths exchange and index exchange as two collectives (separate offset_xchg / idx_xchg "
+                         "rows) instead of the one device-side call")
+    ap.add_argument("--unfused-forward", action="store_true",
+                    help="lookup kernel, then the push kernel (separate emb_lookup / fwd_a2a rows)")
     ap.add_argument("--compare-nccl", action="store_true")
     ap.add_argument("--json", action="store_true")
     return ap.parse_args(argv)
 
 
 def run(argv=None):
+    import time
     args = _parse(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
@@ -337,44 +466,124 @@ def run(argv=None):
     rows = parse_embedding_sizes(args.arch_embedding_size)
     E, b, L = args.arch_sparse_feature_size, args.mini_batch_size, args.num_indices_per_lookup
     model = DLRMParallelEmbedding(group, rows, E, b, L, dev, lr=args.lr, seed=1)
-    regions = ["offset_idx_xchg", "emb_lookup_fwd_a2a", "bwd_a2a_emb_update", "iter_time"]
-    samples = {k: [] for k in regions}
+    # dense part: one random [out, in] tensor per MLP layer, all-reduced every iteration — the data-parallel
+    # gradient exchange of the reference (initializeData dlrm.py:307-360, stages :1266-1281 / :1303-1317).
+    # Not on the a2a path: plain NCCL all_reduce, async within a stage, the stage closed by a barrier.
+    bot = [int(v) for v in args.arch_mlp_bot.split("-") if v]
+    top = top_mlp_dims(len(rows), bot, [int(v) for v in args.arch_mlp_top.split("-") if v],
+                       args.arch_interaction_op, args.arch_interaction_itself, args.arch_project_size)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    top_layers = [torch.rand(s, generator=g, device=dev) for s in mlp_layer_shapes(top)]
+    bot_layers = [torch.rand(s, generator=g, device=dev) for s in mlp_layer_shapes(bot)]
+    mem_top = sum(t.numel() * t.element_size() for t in top_layers)
+    mem_bot = sum(t.numel() * t.element_size() for t in bot_layers)
+
+    def drain():
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+
+    def all_reduce_stage(layers):
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in layers]
+        for w in works:
+            w.wait()
+        drain()
+
+    lat, mem, dev_ms = [], [], {"offset_idx_xchg": [], "emb_lookup_fwd_a2a": [], "bwd_a2a_emb_update": [],
+                                "iter_time": []}
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     grad = None
     for it in range(args.warmup_batches + args.num_batches):
         batch = SparseBatch.synthetic(rows, b, L, args.num_indices_per_lookup_fixed, seed=rank * 1000 + it,
                                       device=dev, alpha=args.alpha)
-        dist.barrier(group)
-        torch.cuda.synchronize()
+        drain()
+        m, sizes = {}, dict.fromkeys(SIZED_REGIONS, 0)
+
+        def mark(name, sync=False):
+            if sync or args.perf_debug:
+                torch.cuda.synchronize(dev)
+            m[name] = time.monotonic()
+
         e = [ev() for _ in range(4)]
+        mark("iter_start")
         e[0].record()
-        offsets, indices = model.sparse_data_dist(batch)
+        # lengths are the native form of SparseBatch and the inputs are generated on the device: the reference's
+        # calculateLengths and host-to-device push (dlrm.py:254-277) have no counterpart — both rows read ~0
+        mark("length_calc_end")
+        mark("mem_push_idx_end")
+        sizes["offset_xchg"] = batch.lengths.numel() * 8
+        sizes["idx_xchg"] = batch.indices.numel() * 8
+        mark("offset_xchg_start")
+        if args.two_collective_dist:
+            offsets, indices = model.sparse_data_dist(batch, device_side=False, mark=mark)
+        else:
+            offsets, indices = model.sparse_data_dist(batch, device_side=True)
+            mark("offset_xchg_end")
+            mark("idx_xchg_start")       # one call does both exchanges: the index row is empty by construction
+            mark("idx_xchg_end")
         e[1].record()
-        out = model.forward(offsets, indices)
+        drain()
+        mark("bef_emb_lookup")
+        sizes["fwd_a2a"] = sizes["bwd_a2a"] = model.N * model.T_local * E * 4
+        # fused (default): lookup and exchange are one kernel, so the gap row reads ~0 and fwd_a2a holds both
+        out = model.forward(offsets, indices, fused=not args.unfused_forward,
+                            before_exchange=lambda: mark("fwd_a2a_start"))
+        mark("fwd_a2a_end")
         e[2].record()
         if grad is None:
             grad = torch.ones_like(out)
+        mark("grad_push_start")
+        drain()
+        mark("bwd_top_ar_start")
+        sizes["bwd_top_ar"] = mem_top
+        all_reduce_stage(top_layers)
+        mark("bwd_top_ar_end")
+        e_b0 = ev()
+        e_b0.record()
+        mark("bwd_a2a_start")
         model.backward(grad)
-        e[3].record()
-        torch.cuda.synchronize()
+        mark("bwd_a2a_end", sync=True)   # tempB.backward(C) returns with the update queued; drained here so the
+        e[3].record()                    # row holds the exchange + update, not the enqueue time
+        mark("bwd_bot_ar_start")
+        sizes["bwd_bot_ar"] = mem_bot
+        all_reduce_stage(bot_layers)
+        mark("bwd_bot_ar_end")
+        torch.cuda.synchronize(dev)
         if it >= args.warmup_batches:
-            samples["offset_idx_xchg"].append(e[0].elapsed_time(e[1]))
-            samples["emb_lookup_fwd_a2a"].append(e[1].elapsed_time(e[2]))
-            samples["bwd_a2a_emb_update"].append(e[2].elapsed_time(e[3]))
-            samples["iter_time"].append(e[0].elapsed_time(e[3]))
+            t = region_times_us(m)
+            lat.append([t[name] for name, _, _ in REGIONS])
+            mem.append([float(sizes.get(name, 0)) for name, _, _ in REGIONS])
+            dev_ms["offset_idx_xchg"].append(e[0].elapsed_time(e[1]))
+            dev_ms["emb_lookup_fwd_a2a"].append(e[1].elapsed_time(e[2]))
+            dev_ms["bwd_a2a_emb_update"].append(e_b0.elapsed_time(e[3]))
+            dev_ms["iter_time"].append(e[0].elapsed_time(e[3]))
     if model.window.error():
         raise PB200Error("a peer wait timed out during the run")
     stats = {}
-    for k, v in samples.items():
+    for k, v in dev_ms.items():
         t = torch.tensor(v, device=dev).median().view(1)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         stats[k + "_ms_p50_max_rank"] = float(t.item())
+    # the reference's report: every rank's samples gathered, percentiles over all of them (dlrm.py:1039-1066)
+    lat_t = torch.tensor(lat, dtype=torch.float64, device=dev).t().contiguous()       # [R, iters]
+    mem_t = torch.tensor(mem, dtype=torch.float64, device=dev).t().contiguous()
+    lat_all = [torch.empty_like(lat_t) for _ in range(world)]
+    mem_all = [torch.empty_like(mem_t) for _ in range(world)]
+    dist.all_gather(lat_all, lat_t, group=group)
+    dist.all_gather(mem_all, mem_t, group=group)
     if rank == 0:
+        rows_all, rows_mean = percentile_rows(torch.stack(lat_all).cpu(), torch.stack(mem_all).cpu())
+        stats["regions_us_p50"] = {r[0]: round(r[3], 3) for r in rows_all}
         if args.json:
             print(json.dumps(stats))
         else:
+            print(format_report(args.num_batches, rows_all))
+            print("\n\n " + "-" * 125 + "\n\n")
+            print(format_report(args.num_batches, rows_mean))
+            print()
             for k, v in stats.items():
-                print(f"{k:40s} {v:10.3f} ms")
+                if k.endswith("_ms_p50_max_rank"):
+                    print(f"device time {k:40s} {v:10.3f} ms")
     dist.barrier(group)
     return stats
 

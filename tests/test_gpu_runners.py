@@ -56,6 +56,16 @@ def test_dlrm_pattern_runner_world1(cuda_device):
                 "--json"], 29705)
     rec = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
     assert rec["iter_time_ms_p50_max_rank"] > 0 and "offset_idx_xchg_ms_p50_max_rank" in rec
+    # the reference's 21 report rows (dlrm.py:1015-1037) incl. the two MLP all-reduce stages
+    reg = rec["regions_us_p50"]
+    assert len(reg) == 21 and reg["iter_time"] > 0 and reg["bwd_a2a"] > 0 and reg["bwd_top_ar"] > 0 and reg["bwd_bot_ar"] > 0
+    out = _run(["-m", "param_b200.comms.pt.dlrm", "--mini-batch-size", "128", "--num-batches", "2",
+                "--warmup-batches", "1", "--arch-embedding-size", "5000x4", "--arch-sparse-feature-size", "32",
+                "--num-indices-per-lookup", "4", "--arch-mlp-bot", "13-64-32", "--arch-mlp-top", "64-1",
+                "--two-collective-dist", "--unfused-forward", "--perf-debug"], 29715)
+    rows = [ln.split() for ln in out.splitlines() if ln.startswith("\t2\t")]
+    assert len(rows) == 2 * 22 and rows[3][1] == "offset_xchg" and rows[21][1] == "total_time"
+    assert float(rows[5][4]) > 0 and float(rows[7][4]) > 0        # idx_xchg and the lookup gap are real rows here
 
 
 @pytest.mark.parametrize("direction", ["forward", "backward"])

@@ -97,6 +97,50 @@ def test_split_helpers_match_reference():
                 assert (ref_sl.start, ref_sl.stop) == (owner_slice(r, splits).start, owner_slice(r, splits).stop)
 
 
+def test_dlrm_report_regions_and_mlp_shapes_match_the_reference():
+    """The runner's 21 region rows, MLP stage shapes and report layout (dlrm.py:400-411, 575-604, 961-1009,
+    1015-1037, 1069-1177)."""
+    from param_b200.comms.pt import dlrm as mine
+    names = [r[0] for r in mine.REGIONS]
+    assert len(names) == 21 and names[3] == "offset_xchg" and names[16] == "iter_time" and names[-1] == "iter_bwd_a2a"
+    assert all(a in mine.MARKS and b in mine.MARKS for _, a, b in mine.REGIONS)
+    assert mine.mlp_layer_shapes([13, 512, 256, 128]) == [[512, 13], [256, 512], [128, 256]]
+    # 26 tables + the dense feature, bottom MLP ends at 128: 27*26/2 + 128 = 479 inputs to the top MLP
+    assert mine.top_mlp_dims(26, [13, 512, 256, 128], [1024, 1]) == [479, 1024, 1]
+    assert mine.top_mlp_dims(26, [13, 512, 256, 128], [1024, 1], interaction_itself=True)[0] == 27 * 28 // 2 + 128
+    assert mine.top_mlp_dims(3, [4, 3, 2], [4, 2, 1], "cat")[0] == 8
+    with pytest.raises(Exception):
+        mine.top_mlp_dims(3, [4, 3, 2], [4, 2, 1], "sum")
+    marks = {k: 0.001 * i for i, k in enumerate(mine.MARKS)}
+    t = mine.region_times_us(marks)
+    assert abs(t["iter_time"] - 16000.0) < 1e-6 and abs(t["offset_xchg"] - 1000.0) < 1e-6
+    assert abs(t["iter_data_prep"] - 7000.0) < 1e-6 and abs(t["bwd_a2a"] - 1000.0) < 1e-6
+    W, R, n = 2, len(mine.REGIONS), 4
+    lat = torch.arange(W * R * n, dtype=torch.float64).view(W, R, n)
+    mem = torch.zeros(W, R, n, dtype=torch.float64)
+    mem[:, 3, :] = 4096
+    rows_all, rows_mean = mine.percentile_rows(lat, mem)
+    assert rows_all[3][0] == "offset_xchg" and rows_all[3][1] == 4096 and rows_all[0][1] == 0
+    assert rows_all[3][2] == float(lat[:, 3, :].min()) and rows_all[3][3] == float(np.percentile(lat[:, 3, :].numpy(), 50))
+    # running sum(p50) skips the iter_* rows, as the reference's does
+    assert rows_all[16][6] == rows_all[15][6] == rows_all[20][6]
+    assert rows_mean[5][3] == float(np.percentile(lat[:, 5, :].mean(dim=1).numpy(), 50))
+    text = mine.format_report(n, rows_all)
+    lines = [ln for ln in text.split("\n") if ln.strip()]
+    assert lines[0].split()[:2] == ["iters", "region"] and "total_time" in lines[-1] and len(lines) == 23
+    if REF.exists():
+        from make_golden import _ref_paths
+        _ref_paths()
+        import dlrm as ref_dlrm
+        bench = ref_dlrm.commsDLRMBench()
+        timers = bench.initTimers()
+        assert list(bench.measured_regions) == names and set(timers) == set(mine.MARKS)
+        for name, a, b in mine.REGIONS:
+            assert (bench.measured_regions[name]["start"], bench.measured_regions[name]["end"]) == (a, b)
+        ref_mlp = ref_dlrm.paramDLRM_Net.create_mlp(None, 1, np.array([13, 512, 256, 128]))
+        assert [list(map(int, x)) for x in ref_mlp] == mine.mlp_layer_shapes([13, 512, 256, 128])
+
+
 def test_sparse_batch_from_offsets_matches_reference_calculate_lengths(golden_dir):
     from param_b200.comms.pt.dlrm import SparseBatch
     d = np.load(golden_dir / "dlrm_sparse_ref.npz")
