@@ -392,7 +392,7 @@ def run_b200(args):
         "clocks": clk.summary(),
     }
     if rank == 0 and not args.skip_e2e:
-        res["e2e"] = run_e2e(args, arena, idx, off, lookups)
+        res["e2e"], res["e2e_full_output"] = run_e2e(args, arena, idx, off, lookups)
     if rank == 0 and world == 1 and not args.skip_cpu:
         res["cpu_baseline"] = cpu_baseline(args, arena, idx, rows, backward=True)
     if rank == 0 and world == 1 and args.alpha > 0 and not args.skip_uniform:
@@ -414,8 +414,11 @@ def run_b200(args):
 
 
 def run_e2e(args, arena, idx, off, lookups):
-    """Same step through the C-ABI host-buffer entry: indices/offsets start in pinned HOST memory,
-    pooled vectors end in pinned HOST memory; H2D + kernels + D2H are all inside the timed region."""
+    """Same step through the C-ABI host-buffer entries: indices/offsets start in pinned HOST memory and the step's
+    result ends in pinned HOST memory; H2D + kernels + D2H are all inside the timed region.  Two forms:
+    loss (pb200_tbe_step_host_loss): what comes back is the step's scalar result, one sum per table — the pooled
+      vectors stay in HBM as they do in the reference's GPU loop (pytorch_emb.py:48-69) and DLRM step;
+    full_output (pb200_tbe_step_host): all pooled vectors are copied back ([T, B, D], PCIe-bound)."""
     import ctypes as C
     from param_b200 import _cabi
     T, B, L, D = args.tables, args.batch, args.bag, args.dim
@@ -426,31 +429,54 @@ def run_e2e(args, arena, idx, off, lookups):
     h_idx.copy_(idx)
     h_off.copy_(off)
     h_out = torch.empty((T, B, D), dtype=torch.float32).pin_memory()   # [T, B, D]: contiguous D2H per group
+    h_loss = torch.zeros(T, dtype=torch.float64).pin_memory()
     tro_h = arena.row_offsets.cpu()
     ctx = C.c_void_p()
     _cabi.check(lib.pb200_host_ctx_create(C.byref(ctx), g * B * L + 16, g * B, D), "host_ctx_create")
 
-    def call():
+    def call_full(do_bwd=1):
         _cabi.check(lib.pb200_tbe_step_host(ctx, arena.weights.data_ptr(), arena.row_offsets.data_ptr(),
                                             tro_h.data_ptr(), T, D, h_idx.data_ptr(), h_idx.numel(),
                                             h_off.data_ptr(), B, 0, h_out.data_ptr(), 1, g,
-                                            1, C.c_float(-args.lr)), "tbe_step_host")
+                                            do_bwd, C.c_float(-args.lr)), "tbe_step_host")
 
-    for _ in range(2):
-        call()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    n = max(3, args.steps // 2)
-    for _ in range(n):
-        call()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / n
+    def call_loss(do_bwd=1):
+        _cabi.check(lib.pb200_tbe_step_host_loss(ctx, arena.weights.data_ptr(), arena.row_offsets.data_ptr(),
+                                                 tro_h.data_ptr(), T, D, h_idx.data_ptr(), h_idx.numel(),
+                                                 h_off.data_ptr(), B, 0, h_loss.data_ptr(), g,
+                                                 do_bwd, C.c_float(-args.lr)), "tbe_step_host_loss")
+
+    def timed(call):
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = max(3, args.steps // 2)
+        for _ in range(n):
+            call()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    h2d = int(h_idx.numel() * 8 + h_off.numel() * 8)
+    dt_loss = timed(call_loss)
+    # the sums that come back are those of what the full-output form hands back (forward only: same arena state)
+    call_loss(0)
+    call_full(0)
+    ref = h_out[:8].to(torch.float64).sum(dim=(1, 2))
+    loss_ok = bool(torch.allclose(h_loss[:8], ref, rtol=1e-9, atol=1e-9))
+    dt_full = timed(call_full)
     lib.pb200_host_ctx_destroy(ctx)
-    return {"value": lookups / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(h_idx.numel() * 8 + h_off.numel() * 8),
-            "d2h_bytes_per_step": int(h_out.numel() * 4),
+    e2e = {"value": lookups / dt_loss, "unit": UNIT, "ms_per_step": dt_loss * 1e3,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_loss.numel() * 8),
+           "result": "per-table loss (sum of the pooled vectors, float64), checked against the full-output form: %s"
+                     % loss_ok,
+           "path": "pb200_tbe_step_host_loss (C ABI, pinned host buffers, %d-table pipeline groups): "
+                   "H2D indices+offsets -> lookup fwd -> per-table sum -> scatter-add bwd -> D2H loss" % g}
+    full = {"value": lookups / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_out.numel() * 4),
             "path": "pb200_tbe_step_host (C ABI, pinned host buffers, %d-table pipeline groups): "
                     "H2D indices+offsets -> lookup fwd -> D2H pooled -> scatter-add bwd" % g}
+    return e2e, full
 
 
 def cpu_baseline(args, arena, idx, rows, backward):

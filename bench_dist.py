@@ -225,37 +225,51 @@ def run_dist(args):
 
 
 def e2e_dist(args, model, batch, lookups_rank, world, maxr):
-    """Through the public API from HOST buffers: this rank's sparse inputs start in pinned host
-    memory, the batch-parallel pooled tensor ends in pinned host memory."""
+    """Through the public API from HOST buffers: this rank's sparse inputs start in pinned host memory; what ends
+    in pinned host memory is the step's scalar result — the sum of this rank's batch-parallel pooled tensor
+    (pb200_pooled_sum per sample row, then one add over the rows), as the reference's step keeps the pooled
+    tensor on the device for the layers above (dlrm.py:1239-1257).  The form that copies the whole pooled tensor
+    back is timed beside it (`full_output`)."""
     import time
-    dev = model.device
+    from param_b200 import ops
+    from param_b200.comms.pt.dlrm import SparseBatch
     h_len = batch.lengths.cpu().pin_memory()
     h_idx = batch.indices.cpu().pin_memory()
     d_len, d_idx = torch.empty_like(batch.lengths), torch.empty_like(batch.indices)
-    from param_b200.comms.pt.dlrm import SparseBatch
     h_out = torch.empty((model.b, model.T_global * model.E), dtype=torch.float32).pin_memory()
+    h_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
 
-    def call():
+    def call(full):
         d_len.copy_(h_len, non_blocking=True)
         d_idx.copy_(h_idx, non_blocking=True)
         sb = SparseBatch(batch.count, batch.batch_size, d_len, d_idx)
         offsets, indices = model.sparse_data_dist(sb)
         out = model.forward(offsets, indices)
-        h_out.copy_(out, non_blocking=True)
+        if full:
+            h_out.copy_(out, non_blocking=True)
+        else:
+            h_loss.copy_(ops.pooled_sum(out, out.shape[0]).sum(dim=0, keepdim=True), non_blocking=True)
         model.backward(out)
 
-    for _ in range(2):
-        call()
-    torch.cuda.synchronize()
-    dist.barrier()
-    n = max(3, args.steps // 2)
-    t0 = time.perf_counter()
-    for _ in range(n):
-        call()
-    torch.cuda.synchronize()
-    dt = maxr((time.perf_counter() - t0) / n)
+    def timed(full):
+        for _ in range(2):
+            call(full)
+        torch.cuda.synchronize()
+        dist.barrier()
+        n = max(3, args.steps // 2)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            call(full)
+        torch.cuda.synchronize()
+        return maxr((time.perf_counter() - t0) / n)
+
+    dt = timed(False)
+    dt_full = timed(True)
+    h2d = int((h_len.numel() + h_idx.numel()) * 8)
     return {"value": world * lookups_rank / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int((h_len.numel() + h_idx.numel()) * 8),
-            "d2h_bytes_per_step": int(h_out.numel() * 4),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+            "result": "loss = sum of the rank's pooled [lN, T_g*E] tensor (float64)",
+            "full_output": {"value": world * lookups_rank / dt_full, "ms_per_step": dt_full * 1e3,
+                            "d2h_bytes_per_step": int(h_out.numel() * 4)},
             "path": "DLRMParallelEmbedding: H2D lengths+indices -> sparse_data_dist (2 peer-push a2a + regroup) -> "
-                    "lookup -> fused a2a -> D2H pooled -> transpose a2a -> scatter-add"}
+                    "fused lookup + a2a -> pooled sum -> D2H loss -> transpose a2a -> scatter-add"}

@@ -450,6 +450,28 @@ int pb200_tbe_step_host(pb200_host_ctx *ctx, float *weights_dev,
                         const int64_t *offsets_host, int64_t batch,
                         int32_t pool_mode, float *out_host, int32_t out_layout,
                         int32_t tables_per_group, int32_t do_bwd, float bwd_scale);
+/* Loss form of the training step: what leaves the device is the step's scalar result, not the pooled
+ * vectors — loss_host[t] = sum over the batch and the embedding dimension of table t's pooled vectors,
+ * accumulated in double in a fixed order ([num_tables] doubles, host memory).  The pooled vectors stay
+ * in HBM, as they do in the reference's GPU loop (train/compute/pt/pytorch_emb.py:48-69 measure_gpu
+ * leaves `results` on the device) and in its DLRM step, where they feed the all-to-all
+ * (train/comms/pt/dlrm.py:1239-1253).  H2D of indices + offsets, lookup, per-table sum, (do_bwd) the
+ * scatter-add, and the D2H of the sums all happen inside the call.  dim must be a multiple of 4. */
+int pb200_tbe_step_host_loss(pb200_host_ctx *ctx, float *weights_dev,
+                             const int64_t *table_row_offsets_dev, const int64_t *table_row_offsets_host,
+                             int32_t num_tables, int32_t dim,
+                             const int64_t *indices_host, int64_t n_indices,
+                             const int64_t *offsets_host, int64_t batch,
+                             int32_t pool_mode, double *loss_host,
+                             int32_t tables_per_group, int32_t do_bwd, float bwd_scale);
+
+/* The reduction the loss form uses, on device pointers: sums_dev[i] = sum of the block_elems floats of block i
+ * of pooled_dev (n_blocks contiguous blocks), accumulated in double in a fixed order (32 slices per block, an
+ * xor-shuffle tree per slice, slices added in order) — run to run identical.  block_elems must be a multiple of
+ * 4 and pooled_dev 16 B-aligned.  Asynchronous on `stream`. */
+int64_t pb200_pooled_sum_scratch_bytes(int64_t n_blocks);
+int pb200_pooled_sum(const float *pooled_dev, int64_t n_blocks, int64_t block_elems, double *sums_dev,
+                     void *scratch_dev, int64_t scratch_bytes, void *stream);
 
 /* =========================================================================
  * 8. Synthetic data on the device (benchmark support, not on the parity path)

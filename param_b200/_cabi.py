@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_a2a_pooled_bwd_part", "pb200_tbe_fwd_a2a",
     "pb200_regroup_scratch_bytes", "pb200_regroup_sparse", "pb200_sparse_data_dist",
     "pb200_host_ctx_create", "pb200_host_ctx_destroy", "pb200_tbe_fwd_host", "pb200_tbe_step_host",
+    "pb200_tbe_step_host_loss", "pb200_pooled_sum_scratch_bytes", "pb200_pooled_sum",
     "pb200_fill_uniform", "pb200_fill_zipf_indices",
 )
 
@@ -121,6 +122,9 @@ def load():
     sig("pb200_tbe_fwd_host", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32)
     sig("pb200_tbe_step_host", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32,
         i32, f32)
+    sig("pb200_tbe_step_host_loss", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32, f32)
+    sig("pb200_pooled_sum_scratch_bytes", i64, i64)
+    sig("pb200_pooled_sum", C.c_int, vp, i64, i64, vp, vp, i64, vp)
     sig("pb200_fill_uniform", C.c_int, vp, i64, f32, f32, u64, vp)
     sig("pb200_fill_zipf_indices", C.c_int, vp, i64, i32, vp, i64, i32, u64, vp)
     if lib.pb200_abi_version() != 2:

@@ -39,6 +39,27 @@ __device__ __forceinline__ float4 ld_row_f4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+// L2 residency control for kernels whose working set is a mix of a re-read block and a stream: a 64-bit
+// cache policy (createpolicy) travels with every access.  kind 0 = evict_normal, 1 = evict_last, 2 = evict_first.
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {
+    unsigned long long pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_row_f4_hint(const float4 *p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_add_f4_hint(float4 *p, const float4 &v, unsigned long long pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
 // Streams read exactly once (indices, offsets, grad rows): do not pollute L1.
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
     float4 v;

@@ -221,6 +221,8 @@ __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long lon
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned cur_key = 0xffffffffu;   // no arena row has this id (row count < 2^32 - 1)
+    const unsigned long long pol_grad = l2_policy(p.l2_hints ? 1 : 0);
+    const unsigned long long pol_row = l2_policy(p.l2_hints ? 2 : 0);
 
     auto flush = [&]() {
         if (cur_key != 0xffffffffu) {
@@ -230,7 +232,7 @@ __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long lon
                 if (col_ok[c]) {
                     float4 v = acc[c];
                     v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-                    red_add_f4(rp + c * G + lane_g, v);
+                    red_add_f4_hint(rp + c * G + lane_g, v, pol_row);
                 }
                 acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -261,7 +263,7 @@ __device__ __forceinline__ void segment_reduce_body(const BwdParams &p, long lon
                 const unsigned goff = __shfl_sync(0xffffffffu, my_goff, src, G);
                 if (SIDE) ww[u] = __shfl_sync(0xffffffffu, my_w, src, G);
 #pragma unroll
-                for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4(colp[c] + goff);
+                for (int c = 0; c < C; ++c) v[u][c] = ld_row_f4_hint(colp[c] + goff, pol_grad);
             }
             const bool all_valid = (j0 + U <= valid) && (j0 + U <= G);
             // every key of the batch must match (the sort may be on the low key bits only, so
@@ -398,6 +400,11 @@ static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows
     pr.table_lo = table_lo;
     pr.table_hi = table_hi;
     pr.idx_is_i32 = idx_type == PB200_IDX_I32;
+    static const int l2_hints = [] {
+        const char *e = getenv("PB200_SEG_L2HINT");
+        return e ? atoi(e) : 0;
+    }();
+    pr.l2_hints = l2_hints;
     const int vec4 = p.dim >> 2;
     const long long n = v.n, n_seg = v.n_seg;
     // segmented reduce of the whole request: ONE launch (the keys are arena rows, globally sorted)

@@ -18,9 +18,63 @@ struct pb200_host_ctx {
     cudaEvent_t ev_h2d[2], ev_k[2], ev_d2h[2], ev_bwd[2];
     void *bwd_scratch;          // sort plan + reducer scratch of the backward (grown on first use)
     long long bwd_scratch_bytes;
+    double *d_loss;             // loss form: [tables] sums + [tables][kLossChunks] partial sums (grown on first use)
+    long long loss_tables;
 };
 
 using namespace pb200;
+
+// ---- loss form: per-table sum of the pooled vectors, the scalar(s) a training step hands back --------
+// Two fixed-shape stages so that the value does not depend on scheduling: CTA (c, t) sums slice c of table t's
+// [B, dim] pooled block in double (strided float4 reads, xor-shuffle tree, warps combined in order), then one
+// thread per table adds the kLossChunks partial sums in order.
+constexpr int kLossChunks = 32;
+constexpr int kLossThreads = 256;
+
+__global__ void __launch_bounds__(kLossThreads) pooled_sum_kernel(const float *__restrict__ pooled,
+                                                                   long long per_table, double *partial) {
+    __shared__ double s_w[kLossThreads / 32];
+    const int t = blockIdx.y, c = blockIdx.x;
+    const long long n4 = per_table >> 2;
+    const long long per = (n4 + kLossChunks - 1) / kLossChunks;
+    const long long lo = (long long)c * per;
+    const long long hi = lo + per < n4 ? lo + per : n4;
+    const float4 *src = (const float4 *)(pooled + (long long)t * per_table);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long long i = lo + threadIdx.x;
+    for (; i + 3 * kLossThreads < hi; i += 4 * kLossThreads) {
+        const float4 v0 = __ldg(src + i), v1 = __ldg(src + i + kLossThreads);
+        const float4 v2 = __ldg(src + i + 2 * kLossThreads), v3 = __ldg(src + i + 3 * kLossThreads);
+        a0 += ((double)v0.x + (double)v0.y) + ((double)v0.z + (double)v0.w);
+        a1 += ((double)v1.x + (double)v1.y) + ((double)v1.z + (double)v1.w);
+        a2 += ((double)v2.x + (double)v2.y) + ((double)v2.z + (double)v2.w);
+        a3 += ((double)v3.x + (double)v3.y) + ((double)v3.z + (double)v3.w);
+    }
+    for (; i < hi; i += kLossThreads) {
+        const float4 v = __ldg(src + i);
+        a0 += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    }
+    double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLossThreads / 32; ++w) sum += s_w[w];
+        partial[(long long)t * kLossChunks + c] = sum;
+    }
+}
+
+__global__ void loss_final_kernel(const double *partial, double *loss, int num_tables) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tables) return;
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < kLossChunks; ++c) sum += partial[(long long)t * kLossChunks + c];
+    loss[t] = sum;
+}
 
 extern "C" int pb200_host_ctx_destroy(pb200_host_ctx *c);
 
@@ -72,22 +126,36 @@ extern "C" int pb200_host_ctx_destroy(pb200_host_ctx *c) {
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->bwd_scratch) cudaFree(c->bwd_scratch);
+    if (c->d_loss) cudaFree(c->d_loss);
     free(c);
     return PB200_OK;
 }
 
-extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
-                                   const int64_t *table_row_offsets_dev,
-                                   const int64_t *table_row_offsets_host, int32_t num_tables,
-                                   int32_t dim, const int64_t *indices_host, int64_t n_indices,
-                                   const int64_t *offsets_host, int64_t batch, int32_t pool_mode,
-                                   float *out_host, int32_t out_layout, int32_t tables_per_group,
-                                   int32_t do_bwd, float bwd_scale) {
-    if (!c || !weights_dev || !table_row_offsets_dev || !indices_host || !offsets_host || !out_host)
-        return PB200_EINVAL;
+// out_host != nullptr: the pooled vectors go back to the host (layout out_layout); loss_host != nullptr: only the
+// per-table sums do ([num_tables] doubles) and the pooled vectors never leave the device
+static int step_host_impl(pb200_host_ctx *c, float *weights_dev, const int64_t *table_row_offsets_dev,
+                          const int64_t *table_row_offsets_host, int32_t num_tables, int32_t dim,
+                          const int64_t *indices_host, int64_t n_indices, const int64_t *offsets_host,
+                          int64_t batch, int32_t pool_mode, float *out_host, int32_t out_layout,
+                          double *loss_host, int32_t tables_per_group, int32_t do_bwd, float bwd_scale) {
+    if (!c || !weights_dev || !table_row_offsets_dev || !indices_host || !offsets_host) return PB200_EINVAL;
+    if ((out_host == nullptr) == (loss_host == nullptr)) return PB200_EINVAL;
     if (num_tables < 1 || dim != c->dim || batch < 1 || tables_per_group < 1) return PB200_EINVAL;
     if (out_layout != 0 && out_layout != 1) return PB200_EINVAL;
     if ((long long)tables_per_group * batch > c->max_bags) return PB200_EINVAL;
+    if (loss_host) {
+        if (dim % 4 != 0) return PB200_EUNSUPPORTED;
+        out_layout = 1;                              // table-major staging: a table's pooled block is contiguous
+        if (num_tables > c->loss_tables) {
+            PB200_CUDA_TRY(cudaStreamSynchronize(c->s_k));
+            if (c->d_loss) cudaFree(c->d_loss);
+            c->d_loss = nullptr;
+            c->loss_tables = 0;
+            PB200_CUDA_TRY(cudaMalloc(&c->d_loss, (size_t)num_tables * (kLossChunks + 1) * sizeof(double)));
+            c->loss_tables = num_tables;
+        }
+    }
+    double *d_partial = c->d_loss ? c->d_loss + num_tables : nullptr;
     // bulk staging wants absolute even index positions 16 B-aligned: keep batch even or fall back
     const int algo = PB200_FWD_AUTO;
     if (do_bwd) {
@@ -145,6 +213,12 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
                                c->d_idx[b] + pad - i_lo, i_hi, c->d_off[b], batch, PB200_IDX_I64,
                                nullptr, pool_mode, c->d_out[b], st_t, st_b, algo, c->s_k);
         if (rc != PB200_OK) return rc;
+        if (loss_host) {
+            pooled_sum_kernel<<<dim3(kLossChunks, (unsigned)tg), kLossThreads, 0, c->s_k>>>(
+                c->d_out[b], (long long)batch * dim, d_partial + (long long)t0 * kLossChunks);
+            PB200_LAUNCH_CHECK();
+            count_launch(1);
+        }
         PB200_CUDA_TRY(cudaEventRecord(c->ev_k[b], c->s_k));
         if (do_bwd) {
             // training step: the pooled vectors double as the incoming gradient (in a real model
@@ -160,7 +234,9 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
         }
 
         PB200_CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->ev_k[b], 0));
-        if (out_layout == 0) {
+        if (loss_host) {
+            // nothing to copy back per group: the event below only marks d_out[b] as consumed
+        } else if (out_layout == 0) {
             // device [B, tg*dim] -> host columns [t0*dim, (t0+tg)*dim) of [B, T*dim]
             PB200_CUDA_TRY(cudaMemcpy2DAsync(out_host + (long long)t0 * dim,
                                              (size_t)num_tables * dim * 4, c->d_out[b],
@@ -175,10 +251,68 @@ extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
         // g+2 waits that H2D, hence transitively this D2H — no extra edge needed, and kernel g+1
         // is free to overlap this D2H.
     }
+    if (loss_host) {
+        loss_final_kernel<<<(num_tables + 127) / 128, 128, 0, c->s_k>>>(d_partial, c->d_loss, num_tables);
+        PB200_LAUNCH_CHECK();
+        count_launch(1);
+        PB200_CUDA_TRY(cudaMemcpyAsync(loss_host, c->d_loss, (size_t)num_tables * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->s_k));
+    }
     PB200_CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
     PB200_CUDA_TRY(cudaStreamSynchronize(c->s_k));
     PB200_CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
     return PB200_OK;
+}
+
+extern "C" int64_t pb200_pooled_sum_scratch_bytes(int64_t n_blocks) {
+    return n_blocks > 0 ? n_blocks * kLossChunks * (int64_t)sizeof(double) : 0;
+}
+
+extern "C" int pb200_pooled_sum(const float *pooled_dev, int64_t n_blocks, int64_t block_elems,
+                                double *sums_dev, void *scratch_dev, int64_t scratch_bytes, void *stream) {
+    if (!pooled_dev || !sums_dev || n_blocks < 1 || block_elems < 1) return PB200_EINVAL;
+    if (block_elems % 4 != 0 || ((uintptr_t)pooled_dev & 15) != 0) return PB200_EUNSUPPORTED;
+    if (n_blocks > 65535 * 1024ll || n_blocks > 0x7fffffffll) return PB200_EUNSUPPORTED;
+    if (!scratch_dev || scratch_bytes < pb200_pooled_sum_scratch_bytes(n_blocks)) return PB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = (double *)scratch_dev;
+    for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {          // grid.y limit
+        const long long nb = n_blocks - b0 < 65535 ? n_blocks - b0 : 65535;
+        pooled_sum_kernel<<<dim3(kLossChunks, (unsigned)nb), kLossThreads, 0, st>>>(
+            pooled_dev + b0 * block_elems, block_elems, partial + b0 * kLossChunks);
+        PB200_LAUNCH_CHECK();
+        count_launch(1);
+    }
+    loss_final_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, st>>>(partial, sums_dev, (int)n_blocks);
+    PB200_LAUNCH_CHECK();
+    count_launch(1);
+    return PB200_OK;
+}
+
+extern "C" int pb200_tbe_step_host(pb200_host_ctx *c, float *weights_dev,
+                                   const int64_t *table_row_offsets_dev,
+                                   const int64_t *table_row_offsets_host, int32_t num_tables,
+                                   int32_t dim, const int64_t *indices_host, int64_t n_indices,
+                                   const int64_t *offsets_host, int64_t batch, int32_t pool_mode,
+                                   float *out_host, int32_t out_layout, int32_t tables_per_group,
+                                   int32_t do_bwd, float bwd_scale) {
+    if (!out_host) return PB200_EINVAL;
+    return step_host_impl(c, weights_dev, table_row_offsets_dev, table_row_offsets_host, num_tables, dim,
+                          indices_host, n_indices, offsets_host, batch, pool_mode, out_host, out_layout,
+                          nullptr, tables_per_group, do_bwd, bwd_scale);
+}
+
+extern "C" int pb200_tbe_step_host_loss(pb200_host_ctx *c, float *weights_dev,
+                                        const int64_t *table_row_offsets_dev,
+                                        const int64_t *table_row_offsets_host, int32_t num_tables,
+                                        int32_t dim, const int64_t *indices_host, int64_t n_indices,
+                                        const int64_t *offsets_host, int64_t batch, int32_t pool_mode,
+                                        double *loss_host, int32_t tables_per_group, int32_t do_bwd,
+                                        float bwd_scale) {
+    if (!loss_host) return PB200_EINVAL;
+    return step_host_impl(c, weights_dev, table_row_offsets_dev, table_row_offsets_host, num_tables, dim,
+                          indices_host, n_indices, offsets_host, batch, pool_mode, nullptr, 1, loss_host,
+                          tables_per_group, do_bwd, bwd_scale);
 }
 
 extern "C" int pb200_tbe_fwd_host(pb200_host_ctx *c, const float *weights_dev,

@@ -65,6 +65,7 @@ struct SortArgs {
     unsigned *bin_total;     // [T][1 << BITS]
     long long *count;        // out: offsets[T * B] - offsets[0]
     int num_tables;
+    int hist_plain;          // histogram kernel: one shared-memory atomic per lookup, no warp aggregation
 };
 
 // Positions p0, p1 are absolute (they address `indices` / `psw`, which the caller may have shifted so that
@@ -150,6 +151,14 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const SortArgs
             unsigned key = 0;
             if (ok[u]) key = FIRST ? (unsigned)ld_index<index_t>(idx_t + rel) : src_t[rel].x;
             d[u] = (key >> a.shift) & (BINS - 1);
+        }
+        if (a.hist_plain) {
+            // digits of a warp's lookups are (nearly) distinct — the low bits of the distinct rows of one or two
+            // bags: aggregation finds nothing to merge and the atomics do not collide
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) atomicAdd(&s_hist[d[u]], 1u);
+            continue;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -492,6 +501,10 @@ static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void 
         const char *e = getenv("PB200_SORT_GROUP");
         return e ? atoi(e) : 0;
     }();
+    static const int hist_plain_env = [] {
+        const char *e = getenv("PB200_SORT_HIST_PLAIN");
+        return e ? atoi(e) : 0;
+    }();
     int group = group_env > 0 ? group_env : p.num_tables;
     if (group > 65535) group = 65535;
 
@@ -527,6 +540,7 @@ static int build_sort_plan_t(const BwdParams &p, long long max_table_rows, void 
         for (int ps = 0; ps < g.passes; ++ps) {
             const bool first = ps == 0, last = ps == g.passes - 1;
             a.shift = g.shift[ps];
+            a.hist_plain = (hist_plain_env & (first ? 1 : 2)) ? 1 : 0;   // bit 0: first pass, bit 1: later passes
             // pass ps writes buffer (passes - 1 - ps) & 1: 0 = out area, 1 = tmp
             uint2 *wr = ((g.passes - 1 - ps) & 1) ? tmp : out_as_pairs;
             const uint2 *rd = ((g.passes - ps) & 1) ? tmp : out_as_pairs;

@@ -153,6 +153,9 @@ struct BwdParams {
     // batch]) - offsets[0] are reduced (read on the device); table_hi <= table_lo: the whole request
     int table_lo, table_hi;
     int idx_is_i32;
+    // SORTED reduce: L2 policies — gradient rows (re-read ~bag-size times while their table is reduced) evict_last,
+    // the read-modify-write of the arena rows (touched once) evict_first.  0: no hints.
+    int l2_hints;
 };
 
 // Builds the plan in `plan` (layout above) on `st`.  Returns a PB200 code; never synchronises.

@@ -538,6 +538,29 @@ def regroup_sparse(lengths: torch.Tensor, indices: torch.Tensor, world: int, tab
 
 
 # --------------------------------------------------------------------------------------
+# per-block sums of pooled vectors (the scalar result of a step)
+# --------------------------------------------------------------------------------------
+def pooled_sum(pooled: torch.Tensor, n_blocks: int = 1) -> torch.Tensor:
+    """float64 [n_blocks]: the sum of each of the n_blocks equal contiguous blocks of `pooled` (fp32), accumulated
+    in double in a fixed order (pb200_pooled_sum).  n_blocks = tables for a [T, B, D] tensor gives per-table
+    sums; n_blocks = rows for a batch-major [B, T*D] tensor gives per-sample sums."""
+    _need_cuda(pooled)
+    if pooled.dtype != torch.float32 or not pooled.is_contiguous():
+        raise PB200Error("pooled_sum takes a contiguous fp32 tensor")
+    n_blocks = int(n_blocks)
+    if n_blocks < 1 or pooled.numel() % n_blocks != 0 or pooled.numel() == 0:
+        raise PB200Error("pooled_sum: the tensor does not split into n_blocks equal blocks")
+    lib = _cabi.load()
+    out = torch.empty(n_blocks, dtype=torch.float64, device=pooled.device)
+    nbytes = int(lib.pb200_pooled_sum_scratch_bytes(n_blocks))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=pooled.device)
+    rc = lib.pb200_pooled_sum(pooled.data_ptr(), n_blocks, pooled.numel() // n_blocks, out.data_ptr(),
+                              scratch.data_ptr(), nbytes, _stream_ptr(pooled))
+    _cabi.check(rc, "pb200_pooled_sum")
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # synthetic data on the device
 # --------------------------------------------------------------------------------------
 def fill_uniform_(t: torch.Tensor, lo: float, hi: float, seed: int) -> torch.Tensor:

@@ -281,6 +281,71 @@ def test_host_buffer_entry(cuda_device, oracle):
     lib.pb200_host_ctx_destroy(ctx)
 
 
+def test_host_buffer_step_loss_form(cuda_device, oracle):
+    """C-ABI §7, loss form: indices/offsets from HOST memory, per-table sums of the pooled vectors back to HOST
+    memory, the scatter-add applied to the resident arena; the full-output form gives the same arena."""
+    import ctypes as C
+    from param_b200 import _cabi, ops
+    rng = np.random.default_rng(22)
+    T, B, L, dim = 7, 192, 6, 64
+    rows, tro, arena, offsets, idx = _random_tbe(rng, T, B, dim, 0, fixed_len=L)
+    lib = _cabi.load()
+    ctx = C.c_void_p()
+    _cabi.check(lib.pb200_host_ctx_create(C.byref(ctx), 3 * B * L + 16, 3 * B, dim))
+    h_idx = torch.from_numpy(idx).pin_memory()
+    h_off = torch.from_numpy(offsets).pin_memory()
+    tro_h = torch.from_numpy(tro)
+    pooled = oracle.tbe_fwd(arena, tro, dim, idx, offsets, B, layout="TBD")          # [T, B, dim]
+    want_loss = pooled.astype(np.float64).sum(axis=(1, 2))
+    scale = -0.05
+    want_w = oracle.tbe_bwd(arena.shape[0], tro, dim, idx, offsets, B, pooled, layout="TBD", scale=scale,
+                            dtype=np.float64, dst=arena.astype(np.float64).copy())
+    results = []
+    for form in ("loss", "full"):
+        ar = ops.TableArena(_t(arena, cuda_device), _t(tro, cuda_device), list(rows), dim)
+        h_loss = torch.zeros(T, dtype=torch.float64).pin_memory()
+        h_out = torch.empty((T, B, dim)).pin_memory()
+        for do_bwd in (0, 1):      # forward only, then the step: the lookup precedes the update, so both see the same arena
+            if form == "loss":
+                _cabi.check(lib.pb200_tbe_step_host_loss(ctx, ar.weights.data_ptr(), ar.row_offsets.data_ptr(),
+                                                         tro_h.data_ptr(), T, dim, h_idx.data_ptr(), idx.size,
+                                                         h_off.data_ptr(), B, 0, h_loss.data_ptr(), 3, do_bwd,
+                                                         C.c_float(scale)))
+                assert np.allclose(h_loss.numpy(), want_loss, rtol=1e-12, atol=1e-9)
+            else:
+                _cabi.check(lib.pb200_tbe_step_host(ctx, ar.weights.data_ptr(), ar.row_offsets.data_ptr(),
+                                                    tro_h.data_ptr(), T, dim, h_idx.data_ptr(), idx.size,
+                                                    h_off.data_ptr(), B, 0, h_out.data_ptr(), 1, 3, do_bwd,
+                                                    C.c_float(scale)))
+                assert np.array_equal(h_out.numpy(), pooled)
+        got = ar.weights.cpu().numpy()
+        assert np.abs(got - want_w).max() <= 1e-5 * max(1.0, np.abs(want_w).max())
+        results.append(got)
+    assert np.array_equal(results[0], results[1])          # same kernels, same order: identical bits
+    # argument errors: both or neither result pointer, dim not a multiple of 4
+    assert lib.pb200_tbe_step_host_loss(ctx, ar.weights.data_ptr(), ar.row_offsets.data_ptr(), tro_h.data_ptr(), T,
+                                        dim, h_idx.data_ptr(), idx.size, h_off.data_ptr(), B, 0, None, 3, 0,
+                                        C.c_float(0.0)) == -1
+    lib.pb200_host_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("shape,blocks", [((5, 33, 64), 5), ((257, 1000), 257), ((3, 4), 1), ((70000, 8), 70000)])
+def test_pooled_sum_matches_float64_numpy(cuda_device, shape, blocks):
+    from param_b200 import ops
+    from param_b200._cabi import PB200Error
+    rng = np.random.default_rng(blocks)
+    x = rng.standard_normal(shape).astype(np.float32)
+    got = ops.pooled_sum(_t(x, cuda_device), blocks).cpu().numpy()
+    want = x.astype(np.float64).reshape(blocks, -1).sum(axis=1)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-10)
+    again = ops.pooled_sum(_t(x, cuda_device), blocks).cpu().numpy()
+    assert np.array_equal(got, again)                       # fixed order: run to run identical
+    with pytest.raises(PB200Error):
+        ops.pooled_sum(_t(x, cuda_device), blocks + 1 if x.size % (blocks + 1) else x.size + 1)
+    with pytest.raises(PB200Error):
+        ops.pooled_sum(torch.from_numpy(x), blocks)
+
+
 def test_tbe_module_fused_sgd(cuda_device, oracle):
     """B200TBE: forward(indices, offsets, per_sample_weights) + out.backward(grad) with the optimizer
     fused into the backward (how pytorch_dist_backend.py:832-857 drives the TBE op)."""

@@ -45,7 +45,8 @@ for what in a.what.split(","):
         elif what == "fwd_staged":
             ops.tbe_forward(arena, idx, off, B, algo="staged", out=out)
         elif what == "bwd_sorted":
-            ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="sorted")
+            ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="sorted",
+                             max_table_rows=a.rows)
         elif what == "bwd_exact":
             ops.tbe_backward(arena.weights, arena.row_offsets, T, D, idx, off, B, out, scale=-1e-6, algo="exact")
         elif what == "bwd_adagrad":
