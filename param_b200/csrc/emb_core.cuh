@@ -162,24 +162,36 @@ struct BagAccum {
             const int col = c * G + lane_g;
             colp[c] = (const V *)p.weights + (col < vec4 ? col : 0);
         }
-        for (int base = 0; base < maxlen; base += G) {
-            // one coalesced read of up to G indices per group; out-of-bag lanes keep row 0 of the
-            // group's table, which is a valid address and masked out below
-            unsigned my_row = (unsigned)base_row;
-            float my_w = 0.f;
-            if (PRELOADED && base == 0) {
-                // first chunk of indices was fetched one bag ahead (software pipeline)
-                my_row = pre_row;
-                my_w = pre_w;
-            } else if (base + lane_g < len) {
+        // one coalesced read of up to G indices per group and chunk; out-of-bag lanes keep row 0 of the
+        // group's table, which is a valid address and masked out below.  The chunk after the current one is
+        // requested before the current chunk's rows are gathered, so a bag longer than G pays the index
+        // latency once, not once per chunk.
+        auto load_chunk = [&](int base, unsigned &row, float &w) {
+            row = (unsigned)base_row;
+            w = 0.f;
+            if (base + lane_g < len) {
                 long long ix;
                 if (FROM_SMEM)
                     ix = (long long)idx_ptr[base + lane_g];
                 else
                     ix = ld_index<index_t>(idx_ptr + base + lane_g);
-                my_row = (unsigned)(base_row + ix);
-                if (WEIGHTED) my_w = ld_stream_f32(psw_ptr + base + lane_g);
+                row = (unsigned)(base_row + ix);
+                if (WEIGHTED) w = ld_stream_f32(psw_ptr + base + lane_g);
             }
+        };
+        unsigned next_row = (unsigned)base_row;
+        float next_w = 0.f;
+        if (PRELOADED) {
+            // first chunk of indices was fetched one bag ahead (software pipeline)
+            next_row = pre_row;
+            next_w = pre_w;
+        } else if (maxlen > 0) {
+            load_chunk(0, next_row, next_w);
+        }
+        for (int base = 0; base < maxlen; base += G) {
+            const unsigned my_row = next_row;
+            const float my_w = next_w;
+            if (base + G < maxlen) load_chunk(base + G, next_row, next_w);
             const int full = min(G, minlen - base);   // rows every group of the warp still has
             const int most = min(G, maxlen - base);   // rows the longest group still has
             int j = 0;

@@ -474,7 +474,20 @@ static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t
     if (vec4 <= 4) return launch_fwd<index_t, 4, 1>(p, algo, st);
     if (vec4 <= 8) return launch_fwd<index_t, 8, 1>(p, algo, st);
     if (vec4 <= 16) return launch_fwd<index_t, 16, 1>(p, algo, st);
-    if (vec4 <= 32) return launch_fwd<index_t, 32, 1>(p, algo, st);
+    if (vec4 <= 32) {
+        // PB200_FWD_GROUP = 16 / 8: two / four bags per warp (16 / 8 lanes per bag, 2 / 4 float4 per lane and row)
+        // instead of one — the same bytes in flight per lane, more independent offsets -> indices -> rows chains
+        // per warp.  DIRECT fp32 only.
+        static const int group_env = [] {
+            const char *e = getenv("PB200_FWD_GROUP");
+            return e ? atoi(e) : 32;
+        }();
+        if (algo == PB200_FWD_DIRECT && !p.weights_f16 && vec4 > 16) {
+            if (group_env == 16) return launch_fwd<index_t, 16, 2>(p, algo, st);
+            if (group_env == 8) return launch_fwd<index_t, 8, 4>(p, algo, st);
+        }
+        return launch_fwd<index_t, 32, 1>(p, algo, st);
+    }
     if (vec4 <= 64) return launch_fwd<index_t, 32, 2>(p, algo, st);
     return launch_fwd<index_t, 32, 4>(p, algo, st);
 }
