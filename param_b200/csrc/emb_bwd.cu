@@ -406,6 +406,10 @@ static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows
         return e ? atoi(e) : 1;
     }();
     pr.l2_hints = l2_hints;
+    static const int seg_group = [] {
+        const char *e = getenv("PB200_SEG_GROUP");
+        return e ? atoi(e) : 32;
+    }();
     const int vec4 = p.dim >> 2;
     const long long n = v.n, n_seg = v.n_seg;
     // segmented reduce of the whole request: ONE launch (the keys are arena rows, globally sorted)
@@ -427,6 +431,7 @@ static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows
     if (vec4 <= 4) PB200_SEG_LAUNCH(4, 1);
     else if (vec4 <= 8) PB200_SEG_LAUNCH(8, 1);
     else if (vec4 <= 16) PB200_SEG_LAUNCH(16, 1);
+    else if (vec4 <= 32 && seg_group == 16) PB200_SEG_LAUNCH(16, 2);   // two segments per warp (trial knob)
     else if (vec4 <= 32) PB200_SEG_LAUNCH(32, 1);
     else if (vec4 <= 64) PB200_SEG_LAUNCH(32, 2);
     else PB200_SEG_LAUNCH(32, 4);

@@ -27,10 +27,10 @@ namespace pb200 {
 // ------------------------------------------------------------------------------------
 // DIRECT variant
 // ------------------------------------------------------------------------------------
-template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float>
+template <typename index_t, int G, int C, bool WEIGHTED, typename WT = float, int UU = 0>
 __device__ __forceinline__ void tbe_fwd_direct_body(const FwdParams &p) {
     constexpr int BPW = 32 / G;  // bags per warp
-    constexpr int U = UnrollFor<C>::value;
+    constexpr int U = UU > 0 ? UU : UnrollFor<C>::value;
     const int lane = threadIdx.x & 31;
     const int lane_g = lane & (G - 1);
     const int grp = lane / G;
@@ -67,6 +67,18 @@ __global__ void __launch_bounds__(256) tbe_fwd_direct_kernel(const FwdParams p) 
 template <typename index_t, int G, int C, bool WEIGHTED>
 __global__ void __launch_bounds__(256, 5) tbe_fwd_direct_kernel_occ5(const FwdParams p) {
     tbe_fwd_direct_body<index_t, G, C, WEIGHTED>(p);
+}
+
+// Two bags per warp for rows of 17..32 float4 (dim 68..128): 16 lanes per bag, 2 float4 per lane and row, 4 rows in
+// flight per lane group, compiled for 5 resident CTAs per SM (48 registers).  Same bytes in flight per lane as the
+// one-bag-per-warp form, but twice as many independent offsets -> indices -> rows chains per warp and 80 instead of
+// 32 bags in flight per SM: the one-bag form was latency x occupancy bound (no unit above 55 %,
+// profiles/r02n_ncu_full_fwd_sort_reduce.md).  Measured at 64 tables (profiles/r02o_*, r02p_*): 3.17 -> 2.51 ms under
+// Zipf 1.15, 5.74 -> 5.71 ms under uniform indices; four bags per warp (8 lanes, 4 float4) 3.10 / 6.41 ms;
+// 4 or 6 resident CTAs and 8 rows in flight within 3 % of the chosen point.  Identical bits (same order of adds).
+template <typename index_t, int G, int C, int MINB, int UU>
+__global__ void __launch_bounds__(256, MINB) tbe_fwd_direct_kernel_var(const FwdParams p) {
+    tbe_fwd_direct_body<index_t, G, C, false, float, UU>(p);
 }
 
 // fp16 tables (fbgemm weights_precision = fp16, split_table_batched_embeddings_ops.py:291): the same
@@ -411,6 +423,14 @@ static int launch_fwd(const FwdParams &p, int algo, cudaStream_t st) {
             const char *e = getenv("PB200_FWD_OCC5");
             return e ? atoi(e) : 0;
         }();
+        if constexpr (G == 16 && C == 2) {
+            if (!p.weights_f16 && !weighted) {
+                tbe_fwd_direct_kernel_var<index_t, G, C, 5, 4><<<(unsigned)grid, 256, 0, st>>>(p);
+                count_launch();
+                PB200_LAUNCH_CHECK();
+                return PB200_OK;
+            }
+        }
         if (p.weights_f16 && weighted)
             tbe_fwd_direct_f16_kernel<index_t, G, C, true><<<(unsigned)grid, 256, 0, st>>>(p);
         else if (p.weights_f16)
@@ -475,17 +495,13 @@ static int dispatch_fwd(FwdParams &p, int algo, long long num_rows, cudaStream_t
     if (vec4 <= 8) return launch_fwd<index_t, 8, 1>(p, algo, st);
     if (vec4 <= 16) return launch_fwd<index_t, 16, 1>(p, algo, st);
     if (vec4 <= 32) {
-        // PB200_FWD_GROUP = 16 / 8: two / four bags per warp (16 / 8 lanes per bag, 2 / 4 float4 per lane and row)
-        // instead of one — the same bytes in flight per lane, more independent offsets -> indices -> rows chains
-        // per warp.  DIRECT fp32 only.
+        // two bags per warp (see tbe_fwd_direct_kernel_var); PB200_FWD_GROUP=32 selects the one-bag form
         static const int group_env = [] {
             const char *e = getenv("PB200_FWD_GROUP");
-            return e ? atoi(e) : 32;
+            return e ? atoi(e) : 16;
         }();
-        if (algo == PB200_FWD_DIRECT && !p.weights_f16 && vec4 > 16) {
-            if (group_env == 16) return launch_fwd<index_t, 16, 2>(p, algo, st);
-            if (group_env == 8) return launch_fwd<index_t, 8, 4>(p, algo, st);
-        }
+        if (algo == PB200_FWD_DIRECT && !p.weights_f16 && !p.psw && vec4 > 16 && group_env == 16)
+            return launch_fwd<index_t, 16, 2>(p, algo, st);
         return launch_fwd<index_t, 32, 1>(p, algo, st);
     }
     if (vec4 <= 64) return launch_fwd<index_t, 32, 2>(p, algo, st);

@@ -38,8 +38,9 @@ struct FusedArgs {
     int world;
 };
 
-template <typename index_t, int G, int C>
-__global__ void __launch_bounds__(256) tbe_fwd_a2a_kernel(const FusedArgs a) {
+// MINB: resident CTAs per SM asked of the compiler (1: no request)
+template <typename index_t, int G, int C, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) tbe_fwd_a2a_kernel(const FusedArgs a) {
     constexpr int BPW = 32 / G;
     constexpr int U = UnrollFor<C>::value;
     __shared__ unsigned long long s_epoch;
@@ -149,9 +150,9 @@ __global__ void __launch_bounds__(256) tbe_fwd_a2a_kernel(const FusedArgs a) {
     }
 }
 
-template <typename index_t, int G, int C>
+template <typename index_t, int G, int C, int MINB = 1>
 static int launch_fused(const FusedArgs &a, int max_ctas, cudaStream_t st) {
-    auto kern = tbe_fwd_a2a_kernel<index_t, G, C>;
+    auto kern = tbe_fwd_a2a_kernel<index_t, G, C, MINB>;
     int per_sm = 1;
     PB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -227,11 +228,17 @@ extern "C" int pb200_tbe_fwd_a2a(pb200_a2a_comm *c, const float *weights,
     if (p.n_bags == 0) return PB200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int vec4 = dim >> 2;
+    // two bags per warp, as in the DIRECT forward (emb_fwd.cu); PB200_FUSED_GROUP=32: one bag per warp
+    static const int fused_group = [] {
+        const char *e = getenv("PB200_FUSED_GROUP");
+        return e ? atoi(e) : 16;
+    }();
 #define PB200_FUSED(IDX)                                                     \
     do {                                                                     \
         if (vec4 <= 4) return launch_fused<IDX, 4, 1>(a, c->max_ctas, st);                \
         if (vec4 <= 8) return launch_fused<IDX, 8, 1>(a, c->max_ctas, st);                \
         if (vec4 <= 16) return launch_fused<IDX, 16, 1>(a, c->max_ctas, st);              \
+        if (vec4 <= 32 && fused_group == 16) return launch_fused<IDX, 16, 2, 5>(a, c->max_ctas, st); \
         if (vec4 <= 32) return launch_fused<IDX, 32, 1>(a, c->max_ctas, st);              \
         if (vec4 <= 64) return launch_fused<IDX, 32, 2>(a, c->max_ctas, st);              \
         return launch_fused<IDX, 32, 4>(a, c->max_ctas, st);                              \
