@@ -184,13 +184,22 @@ class DLRMParallelEmbedding:
         self._side = torch.cuda.Stream(device=device) if self.presort else None
         self._plan, self._plan_buf = None, None
         self.max_table_rows = max(rows) if rows else 0
-        # backward in pieces: the transpose exchange of table group g + 1 (comm stream) runs under the
-        # segmented reduce of group g (PB200_DLRM_BWD_PARTS, default 2; 1 = one exchange, then one reduce)
-        # measured at N = 2 (profiles/r02l_bench_n2*.log): 2 pieces cost 5 % there (3.01 vs 2.86 ms: the exchange is
-        # 0.48 ms, less than what the second epoch + launch costs), so pieces are the default from 4 ranks on,
-        # where the exchange is 1.3 - 2.8 ms
-        default_parts = "2" if self.world >= 4 else "1"
-        self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", default_parts)), min(self.tables_split)))
+        # backward in pieces: the transpose exchange of table group g + 1 (comm stream, grid capped at 32 CTAs so that
+        # it leaves the SMs to the reduce — csrc/a2a.cu, PB200_A2A_PART_CTAS) runs under the segmented reduce of group
+        # g.  Measured (tools/pieces_bench.py, profiles/r02r_pieces_n*.log): N = 8 step 11.9 -> 10.7 ms with 4 parts
+        # (10.6 with 8), N = 4 5.42 -> 4.96 ms with 4 parts; uncapped pushes gain nothing (5.49 ms: a full-grid push
+        # leaves room for one reduce CTA per SM instead of three); parts that do not divide the tables evenly are
+        # slower than no pieces at all (3 / 5 / 6 parts of 64 tables: 6.9 / 6.0 / 6.0 ms).  At N = 2 the exchange
+        # (0.48 ms) is shorter than what a second epoch + launch costs (3.01 vs 2.86 ms) -> one piece there.
+        # PB200_DLRM_BWD_PARTS overrides.
+        t_min = min(self.tables_split)
+        default_parts = 1
+        if self.world >= 4:
+            for cand in (4, 2):
+                if all(t % cand == 0 for t in self.tables_split):
+                    default_parts = cand
+                    break
+        self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", default_parts)), t_min))
         self._comm_stream = torch.cuda.Stream(device=device) if self.bwd_parts > 1 else None
 
     # ---- step 2: SparseDataDist ---------------------------------------------------------------

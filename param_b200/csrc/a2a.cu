@@ -410,7 +410,7 @@ extern "C" int pb200_a2a_comm_destroy(pb200_a2a_comm *comm) {
     return PB200_OK;
 }
 
-int pb200::a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st) {
+int pb200::a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st, int grid_cap) {
     for (int r = 0; r < c->world; ++r) {
         a.peer_data[r] = c->peer_data[r];
         a.peer_pad[r] = c->peer_pad[r];
@@ -424,7 +424,8 @@ int pb200::a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_byt
     a.world = c->world;
     // grid: one CTA per 16 KB of the largest per-peer block, at least 1, at most the SM count
     long long grid = (max_peer_bytes + (16ll << 10) - 1) / (16ll << 10);
-    const int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
+    int cap = c->max_ctas > 0 ? c->max_ctas : sm_count();
+    if (grid_cap > 0 && grid_cap < cap) cap = grid_cap;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     a2a_push_kernel<<<(unsigned)grid, kA2AThreads, 0, st>>>(a);
@@ -623,5 +624,14 @@ extern "C" int pb200_a2a_pooled_bwd_part(pb200_a2a_comm *c, const float *grad, i
         if (bytes > max_peer) max_peer = bytes;
     }
     if (out_window_off + N * T_local * E * 4 > c->window_bytes) return PB200_EINVAL;
-    return a2a_launch_args(c, a, max_peer, (cudaStream_t)stream);
+    // a partial exchange exists to run UNDER the reduce of the previous part: a full grid of 512-thread CTAs
+    // (28 K registers each) would leave room for one reduce CTA per SM instead of three.  The exchange is
+    // NVLink-bound — 32 CTAs reach 90 % of the full grid's bandwidth (profiles/r01_a2a_cta_sweep_n8.log) — so the
+    // partial pushes are capped (PB200_A2A_PART_CTAS, read per call; 0 = no cap).
+    int part_cap = 0;
+    if (parts > 1) {
+        const char *e = getenv("PB200_A2A_PART_CTAS");
+        part_cap = e ? atoi(e) : 32;
+    }
+    return a2a_launch_args(c, a, max_peer, (cudaStream_t)stream, part_cap);
 }

@@ -92,7 +92,8 @@ __device__ __forceinline__ bool wait_flag_ge(const unsigned long long *flag, uns
 namespace pb200 {
 // fills the communicator fields of `a` and launches the push kernel (a2a.cu); shared with the
 // sparse-input redistribution entry (sparse_dist.cu)
-int a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st);
+// grid_cap > 0: at most that many CTAs for this launch (a push that runs under a compute kernel)
+int a2a_launch_args(pb200_a2a_comm *c, A2AArgs &a, long long max_peer_bytes, cudaStream_t st, int grid_cap = 0);
 }  // namespace pb200
 
 struct pb200_a2a_comm {
