@@ -46,11 +46,36 @@ def _stale(target: Path, deps) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+class _BuildLock:
+    """Exclusive advisory lock on build/.lock: N torchrun ranks on a fresh checkout must not compile into the
+    same object files at once — one builds, the others wait and find the library up to date."""
+
+    def __enter__(self):
+        import fcntl
+        (ROOT / "build").mkdir(parents=True, exist_ok=True)
+        self._fh = open(ROOT / "build" / ".lock", "w")
+        fcntl.flock(self._fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._fh, fcntl.LOCK_UN)
+        self._fh.close()
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = _sources()
     hdrs = _headers()
     if not force and not _stale(LIB, srcs + hdrs + [Path(__file__)]):
         return LIB
+    with _BuildLock():
+        # another process may have finished the build while this one waited for the lock
+        if not force and not _stale(LIB, srcs + hdrs + [Path(__file__)]):
+            return LIB
+        return _build_cuda_locked(srcs, hdrs, force, verbose)
+
+
+def _build_cuda_locked(srcs, hdrs, force: bool, verbose: bool) -> Path:
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build {LIB}")
     OBJDIR.mkdir(parents=True, exist_ok=True)
@@ -71,11 +96,15 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", str(LIB), *map(str, objs),
+    # link to a temporary name and rename: a process that dlopens the library never sees a half-written file
+    tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", str(tmp), *map(str, objs),
            "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -66,3 +66,23 @@ def test_no_library_sort_left():
     out = subprocess.run(["cuobjdump", "-sass", str(build.build_cuda())], capture_output=True, text=True).stdout
     assert "DeviceRadixSort" not in out
     assert "radix_scatter_kernel" in out
+
+
+def test_build_lock_is_exclusive_across_processes(tmp_path):
+    """N ranks on a fresh checkout: one builds, the others wait (param_b200/build.py::_BuildLock)."""
+    import subprocess
+    import sys
+    import time
+    code = ("import sys, time; sys.path.insert(0, %r); from param_b200.build import _BuildLock\n"
+            "with _BuildLock():\n"
+            "    open(%r, 'a').write('in %%s %%.3f\\n' %% (sys.argv[1], time.time())); time.sleep(0.6)\n"
+            "    open(%r, 'a').write('out %%s %%.3f\\n' %% (sys.argv[1], time.time()))\n")
+    log = str(tmp_path / "lock.log")
+    code = code % (str(ROOT), log, log)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(i)]) for i in range(3)]
+    assert all(p.wait(timeout=60) == 0 for p in procs)
+    events = [ln.split() for ln in open(log).read().splitlines()]
+    # critical sections never interleave: the log is in/out pairs of the same process
+    assert len(events) == 6
+    for k in range(0, 6, 2):
+        assert events[k][0] == "in" and events[k + 1][0] == "out" and events[k][1] == events[k + 1][1]
