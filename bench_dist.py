@@ -217,7 +217,10 @@ def run_dist(args):
         "clocks": clk.summary(),
     }
     if not args.skip_e2e:
-        res["e2e"] = e2e_dist(args, model, batch, lookups_rank, world, maxr)
+        try:
+            res["e2e"] = e2e_dist(args, model, batch, lookups_rank, world, maxr)
+        except Exception as exc:  # noqa: BLE001 — the device-timed line must survive a failing e2e leg
+            res["e2e"] = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
     if rank == 0:
         print(json.dumps(res))
     dist.barrier()
