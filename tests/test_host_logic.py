@@ -301,6 +301,114 @@ def test_et_replay_builds_b200_ops_from_name_and_schema():
         assert func is not None and out_count == n_out, name
 
 
+def _reference_dlrm_trace_nodes():
+    """fbgemm:: nodes of rank 0 of the reference's own DLRM test trace (et_replay/tests/inputs/dlrm_pytorch_et.tar.gz)"""
+    import io
+    import json
+    import tarfile
+    tar = REF / "et_replay" / "tests" / "inputs" / "dlrm_pytorch_et.tar.gz"
+    with tarfile.open(tar) as tf:
+        member = [m for m in tf.getmembers() if m.name.endswith("dlrm_eg_0.json")][0]
+        nodes = json.load(io.TextIOWrapper(tf.extractfile(member)))["nodes"]
+    return [n for n in nodes if n["name"].startswith("fbgemm::")]
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_fbgemm_named_ops_carry_the_schemas_of_the_reference_dlrm_trace():
+    """The reference's DLRM test trace records the fbgemm_gpu form of the path; the shims must be the ops et_replay
+    would build from those nodes: same names, character-for-character the same schemas, buildable through
+    et_replay_utils.build_torchscript_func (et_replay/et_replay_utils.py:129-212)."""
+    assert _et_replay_importable()
+    import json
+    import types
+    from et_replay import et_replay_utils
+    cfg = json.loads((ROOT / "param_b200" / "et" / "replay-config-b200-fbgemm.json").read_text())
+    for mod in cfg["import modules"]:
+        __import__(mod)
+    from param_b200.et import fbgemm_ops
+    nodes = _reference_dlrm_trace_nodes()
+    names = {n["name"] for n in nodes}
+    assert names == {"fbgemm::" + k for k in fbgemm_ops.SCHEMAS}
+    for n in nodes:
+        short = n["name"].split("::")[1]
+        assert n["op_schema"] == "fbgemm::" + fbgemm_ops.SCHEMAS[short], short
+        held = str(getattr(torch.ops.fbgemm, short).default._schema)
+        assert held.replace(" ", "") == n["op_schema"].replace(" ", ""), short
+        n_out = len(n["outputs"]) if "outputs" in n else len(n.get("output_types", []))
+        if n_out == 0:
+            assert n["name"] in cfg["skip nodes"]            # () -> nothing to rebuild: on the skip list
+            continue
+        node = types.SimpleNamespace(name=n["name"], op_schema=n["op_schema"], id=n["id"],
+                                     input_types=n.get("input_types", n.get("inputs", [])),
+                                     output_types=["y"] * n_out)
+        func, out_count = et_replay_utils.build_torchscript_func(node)
+        assert func is not None and out_count == n_out, short
+
+
+def test_fbgemm_bookkeeping_ops_and_layout_mapping(oracle):
+    """asynchronous_complete_cumsum / permute_2D_sparse_data semantics (they are ATen integer glue and run on CPU
+    tensors), and the mapping of fbgemm's flat weight buffer + per-feature offsets onto a table arena, checked by
+    running the ORACLE lookup on the mapped arguments against a direct per-feature computation."""
+    from param_b200._cabi import PB200Error
+    from param_b200.et import fbgemm_ops as fb
+    rng = np.random.default_rng(5)
+    for dtype in (torch.int32, torch.int64):
+        t = torch.from_numpy(rng.integers(0, 9, size=37)).to(dtype)
+        out = torch.ops.fbgemm.asynchronous_complete_cumsum(t)
+        assert out.dtype == dtype and out.tolist() == [0] + np.cumsum(t.numpy()).tolist()
+    assert torch.ops.fbgemm.asynchronous_complete_cumsum(torch.zeros(0, dtype=torch.int64)).tolist() == [0]
+    # permute: rows repeated, dropped and reordered; with and without weights / the length hint
+    T, B = 5, 4
+    lengths = torch.from_numpy(rng.integers(0, 4, size=(T, B))).to(torch.int32)
+    n = int(lengths.sum())
+    values = torch.arange(100, 100 + n, dtype=torch.int64)
+    weights = torch.from_numpy(rng.standard_normal(n).astype(np.float32))
+    seg = lengths.sum(1).tolist()
+    starts = np.concatenate([[0], np.cumsum(seg)])
+    for perm in ([4, 0, 2, 2, 1], [3], [0, 1, 2, 3, 4], [1, 1, 1]):
+        want_v = np.concatenate([values.numpy()[starts[p]:starts[p + 1]] for p in perm] + [np.zeros(0, np.int64)])
+        want_w = np.concatenate([weights.numpy()[starts[p]:starts[p + 1]] for p in perm] + [np.zeros(0, np.float32)])
+        pl, pv, pw = torch.ops.fbgemm.permute_2D_sparse_data(torch.tensor(perm, dtype=torch.int32), lengths, values,
+                                                             weights, None)
+        assert torch.equal(pl, lengths[perm]) and np.array_equal(pv.numpy(), want_v) and np.array_equal(pw.numpy(), want_w)
+        pl2, pv2, pw2 = torch.ops.fbgemm.permute_2D_sparse_data(torch.tensor(perm, dtype=torch.int32), lengths, values,
+                                                                None, int(want_v.size))
+        assert pw2 is None and torch.equal(pv2, pv) and torch.equal(pl2, pl)
+    # layout: 3 features of dim 8 stored out of order in one flat buffer, with a gap
+    D, rows = 8, [7, 5, 9]
+    elem_off = [5 * D, 0, 16 * D]                      # feature 0 at row 5, feature 1 at row 0, feature 2 at row 16
+    n_w = 27 * D
+    flat = rng.standard_normal(n_w).astype(np.float32)
+    Bq = 6
+    lens = rng.integers(0, 5, size=len(rows) * Bq)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = np.concatenate([rng.integers(0, rows[f], size=int(lens[f * Bq:(f + 1) * Bq].sum())) for f in range(3)]).astype(np.int64)
+    Tn, Bn, Dn, row_off, rows_out = fb.tbe_layout(elem_off, [0, 8, 16, 24], [0, 7, 12, 21], 24, 8, offsets.size, n_w)
+    assert (Tn, Bn, Dn, rows_out) == (3, Bq, D, rows) and row_off == [5, 0, 16, 27]
+    got = oracle.tbe_fwd(flat.reshape(-1, D), np.array(row_off, dtype=np.int64), D, idx, offsets, Bq)
+    want = np.zeros((Bq, 3 * D), dtype=np.float32)
+    for f in range(3):
+        table = flat[elem_off[f]:elem_off[f] + rows[f] * D].reshape(rows[f], D)
+        for b in range(Bq):
+            lo, hi = offsets[f * Bq + b], offsets[f * Bq + b + 1]
+            acc = np.zeros(D, dtype=np.float32)
+            for i in idx[lo:hi]:
+                acc = acc + table[i]
+            want[b, f * D:(f + 1) * D] = acc
+    assert np.array_equal(got, want)
+    for bad in (lambda: fb.tbe_layout(elem_off, [0, 8, 16, 20], [0, 7, 12, 21], 20, 8, offsets.size, n_w),     # mixed dims
+                lambda: fb.tbe_layout([3, 0, 128], [0, 8, 16, 24], [0, 7, 12, 21], 24, 8, offsets.size, n_w),   # off a row
+                lambda: fb.tbe_layout(elem_off, [0, 8, 16, 24], [0, 7, 12, 40], 24, 8, offsets.size, n_w),     # past the end
+                lambda: fb.tbe_layout(elem_off, [0, 8, 16, 24], [0, 7, 12, 21], 24, 8, offsets.size + 1, n_w)):
+        with pytest.raises(PB200Error):
+            bad()
+    # the lookups themselves are CUDA only
+    with pytest.raises(PB200Error):
+        torch.ops.fbgemm.dense_embedding_codegen_lookup_function(
+            torch.from_numpy(flat), torch.tensor(elem_off), torch.tensor([0, 8, 16, 24], dtype=torch.int32), 24, 8,
+            torch.tensor([0, 7, 12, 21]), 5, torch.from_numpy(idx), torch.from_numpy(offsets), 0, None, None, 0)
+
+
 @pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
 def test_et_replay_comm_backend_registers():
     assert _et_replay_importable()
