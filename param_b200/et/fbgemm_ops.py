@@ -89,7 +89,25 @@ def tbe_layout(weights_offsets: List[int], d_offsets: List[int], hash_size_cumsu
     return T, B, D, row_offsets, rows
 
 
+def tbe_layout_even(total_d: int, max_d: int, n_offsets: int, n_weights: int):
+    """The layout used when the metadata tensors carry no layout at all: T = total_D / max_D features of width max_D,
+    the flat buffer cut into T equal tables.  That is the situation of a REPLAYED trace without saved integral tensor
+    data — et_replay fills every integer tensor with ones (tools/et_replay.py:905-941), so D_offsets, weights_offsets
+    and hash_size_cumsum of the recorded call are gone while the scalar arguments and the tensor sizes survive."""
+    D = int(max_d)
+    if D < 4 or D % 4 != 0 or int(total_d) % D != 0:
+        raise PB200Error("fbgemm lookup: total_D / max_D do not describe equal-width features")
+    T = int(total_d) // D
+    if T < 1 or (n_offsets - 1) % T != 0:
+        raise PB200Error("fbgemm lookup: offsets must hold T * B + 1 entries")
+    rows_each = (n_weights // D) // T
+    if rows_each < 1:
+        raise PB200Error("fbgemm lookup: dev_weights is smaller than one row per feature")
+    return T, (n_offsets - 1) // T, D, [f * rows_each for f in range(T)] + [T * rows_each], [rows_each] * T
+
+
 _layout_cache: Dict[tuple, tuple] = {}
+_warned_even = False
 
 
 def _arena(dev_weights, weights_offsets, D_offsets, total_D, max_D, hash_size_cumsum, offsets):
@@ -97,9 +115,22 @@ def _arena(dev_weights, weights_offsets, D_offsets, total_D, max_D, hash_size_cu
            hash_size_cumsum.data_ptr(), int(total_D), int(max_D), offsets.numel())
     hit = _layout_cache.get(key)
     if hit is None:
-        T, B, D, row_off, rows = tbe_layout(weights_offsets.cpu().tolist(), D_offsets.cpu().tolist(),
-                                            hash_size_cumsum.cpu().tolist(), total_D, max_D, offsets.numel(),
-                                            dev_weights.numel())
+        try:
+            T, B, D, row_off, rows = tbe_layout(weights_offsets.cpu().tolist(), D_offsets.cpu().tolist(),
+                                                hash_size_cumsum.cpu().tolist(), total_D, max_D, offsets.numel(),
+                                                dev_weights.numel())
+        except PB200Error:
+            d_off = D_offsets.cpu().tolist()
+            if len(set(d_off)) > 1:          # real metadata that this op does not cover: say so
+                raise
+            # constant-filled metadata: a replayed trace (see tbe_layout_even)
+            global _warned_even
+            if not _warned_even:
+                import warnings
+                warnings.warn("param_b200.et.fbgemm_ops: the lookup's metadata tensors hold no layout (replayed trace "
+                              "without saved integral data?) — dev_weights is cut into total_D / max_D equal tables")
+                _warned_even = True
+            T, B, D, row_off, rows = tbe_layout_even(total_D, max_D, offsets.numel(), dev_weights.numel())
         ro = torch.tensor(row_off, dtype=torch.int64, device=dev_weights.device)
         hit = (T, B, D, ro, rows)
         if len(_layout_cache) > 64:

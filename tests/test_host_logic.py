@@ -402,6 +402,13 @@ def test_fbgemm_bookkeeping_ops_and_layout_mapping(oracle):
                 lambda: fb.tbe_layout(elem_off, [0, 8, 16, 24], [0, 7, 12, 21], 24, 8, offsets.size + 1, n_w)):
         with pytest.raises(PB200Error):
             bad()
+    # a replayed trace without saved integral data: metadata tensors are constant-filled, scalars and sizes survive
+    # (the reference's DLRM test trace: total_D 48, max_D 16, 385 offsets, 640 649 648 weights)
+    Tn, Bn, Dn, row_off, rows_out = fb.tbe_layout_even(48, 16, 385, 640649648)
+    assert (Tn, Bn, Dn) == (3, 128, 16) and rows_out == [13346867] * 3 and row_off == [0, 13346867, 26693734, 40040601]
+    assert row_off[-1] * 16 <= 640649648
+    with pytest.raises(PB200Error):
+        fb.tbe_layout_even(48, 10, 385, 640649648)
     # the lookups themselves are CUDA only
     with pytest.raises(PB200Error):
         torch.ops.fbgemm.dense_embedding_codegen_lookup_function(
