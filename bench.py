@@ -318,9 +318,32 @@ def run_b200(args):
             r["frac_dram"] = round(dram / (ms * 1e-3) / 1e9 / peak, 4)
         return r
 
+    def distinct_rows():
+        """Measured in this run, outside every timed region: how many distinct (table, row) pairs the request touches
+        (torch.unique per table) — what fixes the COMPULSORY DRAM traffic of the request: every distinct row must be
+        read once by the forward, read and written once by the reduce, whatever the caches do."""
+        try:
+            n = 0
+            for t in range(T):
+                n += int(torch.unique(idx[t * B * L:(t + 1) * B * L]).numel())
+            return n
+        except Exception:  # noqa: BLE001 — an extra figure must not take the line down
+            return None
+
+    def with_compulsory(r, ms, nbytes):
+        if nbytes is not None:
+            r["compulsory_bytes"] = int(nbytes)
+            r["frac_dram_compulsory"] = round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)
+        return r
+
     def legs(tag):
         """CUDA-event time of every kernel (group) of the step, same process, same inputs"""
         k = {}
+        nd = distinct_rows()
+        comp_fwd = comp_red = None
+        if nd is not None:
+            comp_fwd = nd * D * 4 + lookups * 8 + (T * B + 1) * 8 + T * B * D * 4     # rows + indices + offsets + output
+            comp_red = T * B * D * 4 + 2 * nd * D * 4 + lookups * 8                   # gradient + row RMW + keys / values
         k["fwd"] = ev_time(fwd, args.steps)
         if bwd_algo != "atomic":
             k["sort_plan"] = ev_time(lambda: plan(exact=bwd_algo == "exact"), args.steps)
@@ -328,12 +351,13 @@ def run_b200(args):
             k["reduce"] = ev_time(lambda: reduce(p), args.steps)
         k["bwd"] = ev_time(bwd, args.steps)
         sfx = "" if tag == "zipf" else "_uniform"
-        r = {"fwd": dict(roof(fwd_bytes, k["fwd"], traffic.get("fwd" + sfx)),
-                         kernel="tbe_fwd_direct_kernel (1 launch/step)",
+        r = {"fwd": dict(with_compulsory(roof(fwd_bytes, k["fwd"], traffic.get("fwd" + sfx)), k["fwd"], comp_fwd),
+                         kernel="tbe_fwd_direct_kernel_var<.., 16, 2, 5, 4>: two bags per warp (1 launch/step)",
                          lookups_per_s=lookups / k["fwd"] * 1e3,
                          param_bw_gbs=round(lookups * D * 4 / k["fwd"] / 1e6, 1))}
         if "reduce" in k:
-            r["bwd_reduce"] = dict(roof(bwd_bytes, k["reduce"], traffic.get("bwd_reduce" + sfx)),
+            r["bwd_reduce"] = dict(with_compulsory(roof(bwd_bytes, k["reduce"], traffic.get("bwd_reduce" + sfx)),
+                                                   k["reduce"], comp_red),
                                    kernel="segment_reduce_kernel (1 launch/step; carries all of the backward's "
                                           "algorithmic bytes: gradient rows in, row read-modify-write)")
             sort_bytes = lookups * 48
