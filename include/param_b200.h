@@ -273,6 +273,14 @@ int pb200_tbe_plan_build(void *scratch, int64_t scratch_bytes,
                          const void *offsets, int64_t batch, int32_t idx_type,
                          const float *psw, int32_t pool_mode,
                          int64_t go_stride_t, int64_t go_stride_b, void *stream);
+/* Host-side query, no CUDA call: the digit plan and tiling pb200_tbe_plan_build uses for a request of this
+ * shape — passes, per-pass digit width and shift (arrays of 4), bags per tile, tiles per table — and the byte
+ * offsets of the sorted keys / values inside the plan buffer.  Everything the host decides about a plan is a
+ * function of these by-value arguments (which is what makes building and consuming it free of device
+ * read-backs); exposed so that it can be checked without a GPU. */
+int pb200_sort_plan_geometry(int64_t n_indices, int32_t num_tables, int64_t batch, int64_t max_table_rows,
+                             int32_t *passes, int32_t *bits, int32_t *shifts, int32_t *tile_bags,
+                             int32_t *tiles_per_table, int64_t *keys_offset, int64_t *vals_offset);
 
 /* =========================================================================
  * 4. Peer-memory all-to-all (single node, NVLink 5 / NVSwitch)

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "pb200_embbag_fwd", "pb200_tbe_fwd", "pb200_tbe_fwd_f16", "pb200_check_indices",
     "pb200_tbe_bwd_scratch_bytes", "pb200_tbe_bwd", "pb200_embbag_bwd_sparse", "pb200_tbe_bwd_tables",
     "pb200_tbe_bwd_fused_scratch_bytes", "pb200_tbe_bwd_fused", "pb200_tbe_plan_build",
+    "pb200_sort_plan_geometry",
     "pb200_a2a_comm_create", "pb200_a2a_comm_destroy", "pb200_a2a_comm_config",
     "pb200_a2a_comm_error", "pb200_a2a_single", "pb200_a2a_list",
     "pb200_a2a_pooled_fwd", "pb200_a2a_pooled_bwd", "pb200_a2a_pooled_bwd_part", "pb200_tbe_fwd_a2a",
@@ -123,6 +124,8 @@ def load():
     sig("pb200_tbe_step_host", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32,
         i32, f32)
     sig("pb200_tbe_step_host_loss", C.c_int, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, i32, f32)
+    p_i32 = C.POINTER(C.c_int32)
+    sig("pb200_sort_plan_geometry", C.c_int, i64, i32, i64, i64, p_i32, p_i32, p_i32, p_i32, p_i32, p_i64, p_i64)
     sig("pb200_pooled_sum_scratch_bytes", i64, i64)
     sig("pb200_pooled_sum", C.c_int, vp, i64, i64, vp, vp, i64, vp)
     sig("pb200_fill_uniform", C.c_int, vp, i64, f32, f32, u64, vp)

@@ -376,6 +376,27 @@ extern "C" int pb200_tbe_plan_build(void *scratch, int64_t scratch_bytes,
     return build_sort_plan(p, idx_type, max_table_rows, scratch, L, (cudaStream_t)stream);
 }
 
+extern "C" int pb200_sort_plan_geometry(int64_t n_indices, int32_t num_tables, int64_t batch,
+                                        int64_t max_table_rows, int32_t *passes, int32_t *bits, int32_t *shifts,
+                                        int32_t *tile_bags, int32_t *tiles_per_table, int64_t *keys_offset,
+                                        int64_t *vals_offset) {
+    if (n_indices < 0 || num_tables < 1 || batch < 1 || !passes || !bits || !shifts || !tile_bags ||
+        !tiles_per_table)
+        return PB200_EINVAL;
+    const SortGeom g = sort_geometry(n_indices, num_tables, batch, max_table_rows);
+    *passes = g.passes;
+    for (int i = 0; i < kSortMaxPasses; ++i) {
+        bits[i] = i < g.passes ? g.bits[i] : 0;
+        shifts[i] = i < g.passes ? g.shift[i] : 0;
+    }
+    *tile_bags = g.tile_bags;
+    *tiles_per_table = g.tiles_per_table;
+    const PlanLayout L = plan_layout(n_indices, num_tables, batch, 0, seg_len_from_env());
+    if (keys_offset) *keys_offset = (int64_t)L.keys;
+    if (vals_offset) *vals_offset = (int64_t)L.vals;
+    return PB200_OK;
+}
+
 namespace pb200 {
 
 static int bwd_sorted(const BwdParams &p, int idx_type, long long max_table_rows, void *scratch,

@@ -86,3 +86,41 @@ def test_build_lock_is_exclusive_across_processes(tmp_path):
     assert len(events) == 6
     for k in range(0, 6, 2):
         assert events[k][0] == "in" and events[k + 1][0] == "out" and events[k][1] == events[k + 1][1]
+
+
+def test_sort_plan_geometry_covers_every_key_width():
+    """The digit plan of the hand-written radix sort (csrc/sort_plan.cuh::sort_geometry) through its host-side query:
+    digits of 8 or 10 bits, contiguous from bit 0, covering the key, with the fewest passes that do; tiles of whole
+    bags (a multiple of 16, at most 2048) that cover the batch; keys / values at fixed offsets of the plan buffer."""
+    import ctypes as C
+    from param_b200 import _cabi
+    lib = _cabi.load()
+
+    def geom(n, T, B, rows):
+        passes, tb, tpt = C.c_int32(), C.c_int32(), C.c_int32()
+        bits, shifts = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        ko, vo = C.c_int64(), C.c_int64()
+        rc = lib.pb200_sort_plan_geometry(n, T, B, rows, C.byref(passes), bits, shifts, C.byref(tb), C.byref(tpt),
+                                          C.byref(ko), C.byref(vo))
+        assert rc == 0
+        return passes.value, list(bits)[:passes.value], list(shifts)[:passes.value], tb.value, tpt.value, ko.value, vo.value
+
+    for key_bits in range(1, 33):
+        rows = (1 << key_bits) if key_bits < 32 else (1 << 32) - 1
+        if key_bits > 1:
+            rows -= 1 if key_bits < 32 else 0          # bits_for(2^k - 1) == k
+        passes, bits, shifts, _, _, _, _ = geom(20 * 1000 * 4, 4, 1000, rows)
+        assert all(b in (8, 10) for b in bits) and len(set(bits)) == 1
+        assert shifts == [i * bits[0] for i in range(passes)]
+        assert sum(bits) >= min(key_bits, 32), (key_bits, bits)
+        # minimal: one pass fewer of the widest digit would not cover the key
+        assert (passes - 1) * 10 < key_bits
+    # the bench shape: 1 M rows = 20 key bits = two 10-bit passes; 10 M rows = three 8-bit passes; unknown = 4 x 8
+    assert geom(256 * 65536 * 20, 256, 65536, 1_000_000)[:2] == (2, [10, 10])
+    assert geom(25 * 65536 * 20, 25, 65536, 10_000_000)[:2] == (3, [8, 8, 8])
+    assert geom(1000, 1, 50, 0)[:2] == (4, [8, 8, 8, 8])
+    for n, T, B in ((256 * 65536 * 20, 256, 65536), (7 * 333 * 3, 7, 333), (5, 1, 5), (64 * 100 * 3000, 64, 100)):
+        _, _, _, tile_bags, tiles, ko, vo = geom(n, T, B, 1000)
+        assert tile_bags % 16 == 0 and 16 <= tile_bags <= 2048 and tiles * tile_bags >= B > (tiles - 1) * tile_bags
+        assert ko == 0 and vo >= n * 4 and vo % 256 == 0
+    assert lib.pb200_sort_plan_geometry(10, 0, 5, 100, None, None, None, None, None, None, None) == -1
