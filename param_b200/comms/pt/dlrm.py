@@ -195,8 +195,11 @@ class DLRMParallelEmbedding:
         t_min = min(self.tables_split)
         default_parts = 1
         if self.world >= 4:
+            # a part must keep the push kernel's row loop busy: it copies one gradient row segment of
+            # (tables of the part) x E x 4 bytes per pass of 512 threads x 16 B = 8 KB (8 parts of 64 tables = 4 KB
+            # segments were slower than 4 parts at N = 4)
             for cand in (4, 2):
-                if all(t % cand == 0 for t in self.tables_split):
+                if all(t % cand == 0 and (t // cand) * self.E * 4 >= 8192 for t in self.tables_split):
                     default_parts = cand
                     break
         self.bwd_parts = max(1, min(int(os.environ.get("PB200_DLRM_BWD_PARTS", default_parts)), t_min))
