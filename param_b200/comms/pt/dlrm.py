@@ -404,30 +404,36 @@ def region_times_us(marks: dict) -> dict:
 def percentile_rows(lat: "torch.Tensor", mem: "torch.Tensor"):
     """lat, mem: [W, R, iters] gathered samples.  Returns (per_sample_rows, per_rank_mean_rows), each a list of
     (region, mem_p50, min, p50, p75, p95, running sum of p50 over the non-'iter' regions) — the two tables the
-    reference prints (dlrm.py:1086-1160): percentiles over all W*iters samples, and over the W per-rank means."""
+    reference prints (dlrm.py:1086-1160): percentiles over all W*iters samples, and over the W per-rank means.
+    Single precision throughout, as there: the reference gathers its samples as float32 tensors and numpy keeps
+    float32 through np.percentile and the running sums, which decides the last printed digit."""
     import numpy as np
+    lat = lat.to(torch.float32)
     W, R, _ = lat.shape
-    rows_all, rows_mean, run_all, run_mean = [], [], 0.0, 0.0
+    rows_all, rows_mean = [], []
+    run_all, run_mean = np.float32(0.0), np.float32(0.0)
     for r in range(R):
         name = REGIONS[r][0]
         samples = lat[:, r, :].reshape(-1).numpy()
-        means = lat[:, r, :].mean(dim=1).numpy()
+        means = np.array([lat[w, r, :].mean() for w in range(W)], dtype=np.float32)
         mem_p50 = float(np.percentile(mem[:, r, :].reshape(-1).numpy(), 50))
-        pa = [float(np.percentile(samples, q)) for q in (50, 75, 95)]
-        pm = [float(np.percentile(means, q)) for q in (50, 75, 95)]
+        pa = [np.percentile(samples, q) for q in (50, 75, 95)]
+        pm = [np.percentile(means, q) for q in (50, 75, 95)]
         if "iter" not in name:
-            run_all += pa[0]
-            run_mean += pm[0]
-        rows_all.append((name, mem_p50, float(samples.min()), *pa, run_all))
-        rows_mean.append((name, mem_p50, float(means.min()), *pm, run_mean))
+            run_all = np.float32(run_all + pa[0])
+            run_mean = np.float32(run_mean + pm[0])
+        rows_all.append((name, mem_p50, float(samples.min()), *(float(v) for v in pa), float(run_all)))
+        rows_mean.append((name, mem_p50, float(means.min()), *(float(v) for v in pm), float(run_mean)))
     return rows_all, rows_mean
 
 
-def format_report(iters: int, rows) -> str:
+def format_report(iters: int, rows, header: bool = True) -> str:
     """The reference's table layout (dlrm.py:1069-1081, 1133-1177): tab-separated, a blank line before the
-    iter_* rows, a total_time footer."""
-    out = ["\t{}\t{:>36}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}".format(
-        "iters", "region", "memory (B)", "Latency(us):min", "p50", "p75", "p95", "sum(p50)")]
+    iter_* rows, a total_time footer.  The reference prints the column header once, above the first table."""
+    out = []
+    if header:
+        out.append("\t{}\t{:>36}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}\t{:>12}".format(
+            "iters", "region", "memory (B)", "Latency(us):min", "p50", "p75", "p95", "sum(p50)"))
     total = 0.0
     for name, mem, lo, p50, p75, p95, run in rows:
         if name == "iter_time":
@@ -591,7 +597,7 @@ def run(argv=None):
         else:
             print(format_report(args.num_batches, rows_all))
             print("\n\n " + "-" * 125 + "\n\n")
-            print(format_report(args.num_batches, rows_mean))
+            print(format_report(args.num_batches, rows_mean, header=False))
             print()
             for k, v in stats.items():
                 if k.endswith("_ms_p50_max_rank"):

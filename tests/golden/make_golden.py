@@ -25,6 +25,11 @@ fixtures are produced by running the reference's own call sites here:
                         ones gradient every row gradient is constant along the row, where fbgemm's rowwise
                         Adagrad (mean over the row of g^2) coincides with the elementwise torch.optim.Adagrad.
                         Generate alone with:  python tests/golden/make_golden.py tbe_optim
+  dlrm_report_ref.npz   the reference's own report printer — commsDLRMBench.reportBenchTime
+                        (train/comms/pt/dlrm.py:1011-1193) — run on seeded synthetic samples of its 21 regions for
+                        1 and for 3 ranks (the all_gather it calls is stood in by a copy of the per-rank sample
+                        arrays); the printed text is the fixture param_b200.comms.pt.dlrm.format_report must equal.
+                        Generate alone with:  python tests/golden/make_golden.py dlrm_report
 """
 from __future__ import annotations
 
@@ -339,7 +344,56 @@ def gen_tbe_rowwise():
     print("wrote tbe_rowwise_adagrad_torch.npz")
 
 
+def gen_dlrm_report():
+    """The text the reference prints for known per-rank samples (both of its tables: percentiles over all samples,
+    and over the per-rank means)."""
+    import contextlib
+    import io
+    _ref_paths()
+    import dlrm as ref_dlrm  # /root/reference/train/comms/pt/dlrm.py
+    rng = np.random.default_rng(20261018)
+    out = {}
+    for world in (1, 3):
+        iters, warm = 6, 2
+        bench = ref_dlrm.commsDLRMBench()
+        bench.initTimers()
+        names = list(bench.measured_regions)
+        lat = (rng.random((world, len(names), iters)) * 5000.0).astype(np.float32)       # microseconds
+        mem = rng.integers(0, 1 << 20, size=(world, len(names), warm + iters)).astype(np.int64)
+        mem[:, [i for i, n in enumerate(names) if "xchg" not in n and "a2a" not in n and "_ar" not in n], :] = 0
+        for i, n in enumerate(names):
+            bench.measured_regions[n]["samples"] = [float(v) for v in lat[0, i]]
+            bench.measured_regions[n]["memory"] = [int(v) for v in mem[0, i]]
+        calls = []
+
+        class _Gather:        # stands in for backendFuncs.all_gather: rank r's tensor is row r of the prepared arrays
+            def all_gather(self, ca):
+                src = lat if not calls else mem
+                calls.append(1)
+                for r in range(world):
+                    ca.opTensor[r].copy_(torch.from_numpy(src[r]).to(ca.opTensor[r].dtype))
+
+            def complete_accel_ops(self, ca):
+                pass
+
+        bench.backendFuncs = _Gather()
+        bench.collectiveArgs = types.SimpleNamespace()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            bench.reportBenchTime(0, warm, iters, world, "cpu")
+        out[f"w{world}_lat"] = lat
+        out[f"w{world}_mem"] = mem
+        out[f"w{world}_warm"] = np.int64(warm)
+        out[f"w{world}_text"] = np.array(buf.getvalue())
+    out["regions"] = np.array(names)
+    np.savez_compressed(HERE / "dlrm_report_ref.npz", **out)
+    print("wrote dlrm_report_ref.npz")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dlrm_report":
+        gen_dlrm_report()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tbe_optim":      # torch only: no reference import needed
         gen_tbe_optim()
         gen_tbe_rowwise()
@@ -353,3 +407,4 @@ if __name__ == "__main__":
     gen_a2a()
     gen_tbe_optim()
     gen_tbe_rowwise()
+    gen_dlrm_report()

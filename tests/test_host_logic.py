@@ -121,10 +121,11 @@ def test_dlrm_report_regions_and_mlp_shapes_match_the_reference():
     mem[:, 3, :] = 4096
     rows_all, rows_mean = mine.percentile_rows(lat, mem)
     assert rows_all[3][0] == "offset_xchg" and rows_all[3][1] == 4096 and rows_all[0][1] == 0
-    assert rows_all[3][2] == float(lat[:, 3, :].min()) and rows_all[3][3] == float(np.percentile(lat[:, 3, :].numpy(), 50))
+    assert rows_all[3][2] == float(lat[:, 3, :].min())
+    assert rows_all[3][3] == float(np.percentile(lat[:, 3, :].to(torch.float32).numpy(), 50))      # single precision, as the reference
     # running sum(p50) skips the iter_* rows, as the reference's does
     assert rows_all[16][6] == rows_all[15][6] == rows_all[20][6]
-    assert rows_mean[5][3] == float(np.percentile(lat[:, 5, :].mean(dim=1).numpy(), 50))
+    assert rows_mean[5][3] == float(np.percentile(lat[:, 5, :].to(torch.float32).mean(dim=1).numpy(), 50))
     text = mine.format_report(n, rows_all)
     lines = [ln for ln in text.split("\n") if ln.strip()]
     assert lines[0].split()[:2] == ["iters", "region"] and "total_time" in lines[-1] and len(lines) == 23
@@ -139,6 +140,25 @@ def test_dlrm_report_regions_and_mlp_shapes_match_the_reference():
             assert (bench.measured_regions[name]["start"], bench.measured_regions[name]["end"]) == (a, b)
         ref_mlp = ref_dlrm.paramDLRM_Net.create_mlp(None, 1, np.array([13, 512, 256, 128]))
         assert [list(map(int, x)) for x in ref_mlp] == mine.mlp_layer_shapes([13, 512, 256, 128])
+
+
+def test_dlrm_report_text_equals_what_the_reference_prints(golden_dir):
+    """Fixture: the reference's own commsDLRMBench.reportBenchTime (dlrm.py:1011-1193) run on seeded samples for 1 and
+    3 ranks (tests/golden/make_golden.py dlrm_report).  Both tables — percentiles over all samples, and over the
+    per-rank means — must come out character for character."""
+    from param_b200.comms.pt import dlrm as mine
+    d = np.load(golden_dir / "dlrm_report_ref.npz")
+    assert [str(n) for n in d["regions"]] == [r[0] for r in mine.REGIONS]
+    for w in (1, 3):
+        lat = torch.from_numpy(d[f"w{w}_lat"])
+        mem = torch.from_numpy(d[f"w{w}_mem"]).to(torch.float64)
+        warm = int(d[f"w{w}_warm"])
+        rows_all, rows_mean = mine.percentile_rows(lat.to(torch.float64), mem[:, :, warm:])   # the runner gathers float64
+        parts = [[ln.rstrip() for ln in part.split("\n") if ln.strip()] for part in str(d[f"w{w}_text"]).split("-" * 125)]
+        ref_all, ref_mean = [p for p in parts if p]
+        got_all = [ln.rstrip() for ln in mine.format_report(lat.shape[2], rows_all).split("\n") if ln.strip()]
+        got_mean = [ln.rstrip() for ln in mine.format_report(lat.shape[2], rows_mean, header=False).split("\n") if ln.strip()]
+        assert got_all == ref_all and got_mean == ref_mean, w
 
 
 def test_sparse_batch_from_offsets_matches_reference_calculate_lengths(golden_dir):
