@@ -450,6 +450,34 @@ def test_et_replay_comm_backend_registers():
     assert cls.all_to_allv is B200CommsMixin.all_to_allv     # replayed alltoall_base lands on the push kernel
 
 
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_generated_basic_trace_parses_with_the_reference_parser(tmp_path):
+    """tools/make_basic_trace.py writes one DLRM step in the reference's basic trace format; the reference's own
+    parser (train/comms/pt/commsTraceParser.py:64-152) must read it, incl. the "compute": "emb_lookup" entries
+    (:137-147) that its replay hands to init_emb_lookup / the backend's emb_lookup."""
+    import json
+    import subprocess
+    from param_b200.integration import refpath
+    refpath.setup()
+    from param_bench.train.comms.pt import commsTraceParser as parser
+    W, T, b, L, E, rows = 4, 8, 64, 5, 32, 1000
+    out = tmp_path / "step.json"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "make_basic_trace.py"), "--world", str(W), "--out", str(out),
+                    "--tables", str(T), "--local-batch", str(b), "--bag", str(L), "--dim", str(E), "--rows", str(rows)],
+                   check=True, capture_output=True)
+    trace = parser.parseTrace(json.loads(out.read_text()), "basic", 0, W)
+    kinds = [(c.comms, c.compute) for c in trace]
+    assert kinds == [("all_to_all", None), ("wait", None), (None, "emb_lookup"), ("all_to_all", None), ("wait", None),
+                     ("all_to_all", None), ("wait", None), (None, "emb_lookup")]
+    idx, fwd, pooled, bwd = trace[0], trace[2], trace[3], trace[7]
+    assert (idx.inMsgSize, idx.outMsgSize, idx.dtype) == (T * W * b * L, T * W * b * L, "long")     # ELEMENTS per rank
+    assert (pooled.inMsgSize, pooled.dtype) == (T * b * W * E, "float") and trace[5].inMsgSize == pooled.inMsgSize
+    for c, direction in ((fwd, "forward"), (bwd, "backward")):
+        assert (c.direction, c.emb_dim, c.num_embs, c.batch_size, c.num_emb_tables_per_device, c.bag_size, c.count) == \
+            (direction, E, rows, b * W, T, L, 1)
+    assert [c.req for c in trace if c.comms] == [0, 0, 1, 1, 2, 2]
+
+
 def test_tbe_request_generator_layout():
     """TBE request layout (split_table_batched_embeddings_ops.py:93-135,191-213): table-major
     indices, cumulative offsets over the concatenation, the reference's alpha regimes."""
