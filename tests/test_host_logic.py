@@ -70,6 +70,27 @@ def test_module_surface_matches_nn_embeddingbag_contract():
         B200EmbeddingBag(10, 4, mode="max")
 
 
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_emb_driver_prints_the_reference_table(capsys, monkeypatch):
+    """run() of the EmbeddingBag driver (train/compute/pt/pytorch_emb.py:208-234): with the measurement stubbed to the
+    same numbers on both sides, the reference's run() and the mirror's print the same text."""
+    import types
+    from make_golden import _ref_paths
+    _ref_paths()
+    import pytorch_emb as ref_emb
+    from param_b200.compute.pt import pytorch_emb as mine
+    dataset = [(4800000, 56, 34, 2048), (1000000, 64, 20, 512), (1024, 8, 1, 1)]
+    fake = {d: (0.0123 * (i + 1), d[3] * d[2] * d[1] * 4) for i, d in enumerate(dataset)}
+    args = types.SimpleNamespace(steps=7)
+    monkeypatch.setattr(ref_emb, "run_single", lambda a, f, e, n, b: fake[(f, e, n, b)])
+    monkeypatch.setattr(mine, "run_single", lambda a, f, e, n, b: fake[(f, e, n, b)])
+    ref_emb.run(args, dataset)
+    want = capsys.readouterr().out
+    mine.run(args, dataset)
+    got = capsys.readouterr().out
+    assert got == want and want.count("\n") == 3 + len(dataset)
+
+
 def test_size_maths():
     from param_b200.comms.pt.comms import get_sizes, parsesize
     assert parsesize("1K") == 1024 and parsesize("1G") == 1 << 30 and parsesize("512") == 512
