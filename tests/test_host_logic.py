@@ -163,6 +163,31 @@ def test_dlrm_report_regions_and_mlp_shapes_match_the_reference():
         assert [list(map(int, x)) for x in ref_mlp] == mine.mlp_layer_shapes([13, 512, 256, 128])
 
 
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_dlrm_runner_flags_carry_the_reference_names(monkeypatch):
+    """Every model / loop flag of param_b200.comms.pt.dlrm exists under the same name in the reference's runner
+    (commsDLRMBench.readArgs, dlrm.py:657-742); what is added here is listed."""
+    import argparse
+    import inspect
+    import re
+    from make_golden import _ref_paths
+    _ref_paths()
+    import dlrm as ref_dlrm
+    from param_b200.comms.pt import dlrm as mine
+    ap = argparse.ArgumentParser()
+    monkeypatch.setattr(sys, "argv", ["dlrm.py"])            # readArgs ends in parser.parse_args() (dlrm.py:733)
+    ref_dlrm.commsDLRMBench().readArgs(ap)
+    ref_flags = {s for a in ap._actions for s in a.option_strings}
+    my_flags = set(re.findall(r'add_argument\("(--[a-z0-9-]+)"', inspect.getsource(mine._parse)))
+    assert my_flags - ref_flags == {"--alpha", "--compare-nccl", "--json", "--lr", "--two-collective-dist",
+                                    "--unfused-forward"}
+    assert {"--arch-mlp-bot", "--arch-mlp-top", "--arch-interaction-op", "--arch-sparse-feature-size",
+            "--arch-embedding-size", "--mini-batch-size", "--num-batches", "--warmup-batches",
+            "--num-indices-per-lookup", "--num-indices-per-lookup-fixed", "--perf-debug"} <= my_flags & ref_flags
+    a = mine._parse(["--arch-mlp-bot", "13-512-256-128", "--arch-mlp-top", "1024-1", "--perf-debug"])
+    assert a.arch_mlp_bot == "13-512-256-128" and a.perf_debug and a.arch_interaction_op == "dot"
+
+
 def test_dlrm_report_text_equals_what_the_reference_prints(golden_dir):
     """Fixture: the reference's own commsDLRMBench.reportBenchTime (dlrm.py:1011-1193) run on seeded samples for 1 and
     3 ranks (tests/golden/make_golden.py dlrm_report).  Both tables — percentiles over all samples, and over the
