@@ -429,6 +429,9 @@ def run_b200(args):
                                        ms_per_step=round(ms_step_u, 4), value=lookups / (ms_step_u * 1e-3),
                                        note="alpha = 0 on the same arena: every row read misses the caches, "
                                             "DRAM traffic ~ algorithmic bytes")
+        # the dominant kernel's HBM-bound figure next to its skewed one, for a reader of `roofline` alone
+        dom_u = roofs_u.get(res["roofline"].get("dominant_kernel"), {})
+        res["roofline"]["uniform_case"] = {k: dom_u.get(k) for k in ("ms", "frac", "frac_dram", "frac_dram_compulsory")}
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
